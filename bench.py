@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""bench.py -- RICK adaptation throughput on B200 (BASELINE.json metric: adapt iters/s, 256 px, batch 2).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (configs[1] of BASELINE.json, named in config.workload): the RICK FFHQ->Babies-shaped loop -- StyleGAN2
+256 px G + D (random init, FFHQ-256 architecture), batch 2 per GPU, 10 synthetic shots, Fisher round every 50
+iterations on 5 images, fisher_quantile 40, prune_quantile 0.1, R1 every 16, path-length every 4, mixing 0.9.
+A "step" is one adaptation iteration (D step [+R1], G step [+path-length], masks, Adam, EMA).  Iteration indices run
+0..W-1 untimed and W..W+K-1 timed with warmup_iter = 0, so a Fisher round falls on iterations 0, 50, ...; the JSON
+line says how many Fisher / R1 / path-length iterations were inside the timed region.
+
+  value   whole-job iters/s with the real images already resident in HBM and no loss read-back
+  e2e     the same loop through the public API with HOST inputs: every step copies its real images from pinned host
+          memory and reads the step's losses back to the host
+  N > 1   one process per GPU (torchrun), DDP-style gradient all-reduce over NCCL, per-GPU batch 2 (weak scaling);
+          value = N x (iterations/s), i.e. batch-2 iteration equivalents per second over the whole job
+  roofline  the package's memory-bound headline kernel (upfirdn2d, BASELINE configs[3] shape (32,512,128,128)->256^2)
+            timed with CUDA events on the launching stream, L2 flushed between launches, against MEASURED_PEAKS.json
+  cpu_baseline / --impl reference   the oracle port of the same iteration on the box's host cores (the reference's
+          CPU path: upfirdn2d_native + native leaky-ReLU semantics), bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOAD = "rick_adapt_ffhq256_b2_10shot_fisher50x5_q40_p0.1"
+METRIC = "adapt_iters_per_s"
+UNIT = "iters/s"
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])), mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def build_networks(size, device, seed=1):
+    """Random init, FFHQ-256 architecture (no checkpoint is available offline); G and G_ema start identical, as after
+    loading one source checkpoint into both (train:876-879)."""
+    from rick_b200 import stylegan2 as sg
+    torch.manual_seed(seed)
+    G = sg.Generator(size, 512, 8)
+    D = sg.Discriminator(size)
+    Ge = sg.Generator(size, 512, 8)
+    De = sg.Discriminator(size)
+    Ge.load_state_dict(G.state_dict())
+    De.load_state_dict(D.state_dict())
+    return G.to(device), D.to(device), Ge.to(device), De.to(device)
+
+
+def synthetic_shots(n, size, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.clamp(torch.randn(n, 3, size, size, generator=g) * 0.5, -1, 1)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+
+def run_ours(args):
+    from rick_b200 import _lib
+    from rick_b200 import dist as rdist
+    from rick_b200.adapt import AdaptConfig, DrawStream, RickAdapter, generate_samples
+
+    rank, world, local_rank = rdist.init_from_env()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback in rick_b200)"
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    lib = _lib.lib()
+    size, batch = 256, 2
+    cfg = AdaptConfig(size=size, batch=batch, warmup_iter=0, fisher_freq=50, num_fisher_img=5, fisher_quantile=40.0,
+                      prune_quantile=0.1, d_reg_every=16, g_reg_every=4, mixing=0.9, lr=0.002)
+    G, D, Ge, De = build_networks(size, device, seed=1)       # identical weights on every rank (DDP)
+    adapter = RickAdapter(cfg, G, D, Ge, De)
+    shots_host = synthetic_shots(10, size, seed=100 + rank).pin_memory()
+    shots_dev = shots_host.to(device)
+    fisher_lat = torch.randn(cfg.num_fisher_img, 512, generator=torch.Generator().manual_seed(7)).to(device)
+    draws = DrawStream(1234 + rank, device, cpu_seeded=False)
+
+    def iteration(i, e2e):
+        if i % cfg.fisher_freq == 0:
+            adapter.fisher_round(fisher_lat, shots_dev[:cfg.num_fisher_img])
+        j = (i * batch) % 10
+        if e2e:
+            real = shots_host[j:j + batch].to(device, non_blocking=True)          # H2D from pinned memory
+        else:
+            real = shots_dev[j:j + batch]
+        out = adapter.step(i, real, draws)
+        if e2e:
+            host = torch.stack([out["d"], out["g"]]).to("cpu")                      # D2H read of the step's losses
+            return host
+        return None
+
+    def timed(first, k, e2e):
+        rdist.barrier()
+        torch.cuda.synchronize()
+        n0 = lib.rick_launch_count()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for i in range(first, first + k):
+            iteration(i, e2e)
+        end.record()
+        torch.cuda.synchronize()
+        rdist.barrier()
+        ms = start.elapsed_time(end)
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, lib.rick_launch_count() - n0
+
+    W, K = args.warmup, args.steps
+    for i in range(W):
+        iteration(i, False)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, launches = timed(W, K, False)
+    ms_e2e, _ = timed(W + K, K, True)
+    clocks = sampler.stop() if rank == 0 else None
+
+    def count(first, k, every):
+        return sum(1 for i in range(first, first + k) if i % every == 0)
+
+    value = world * K / (ms / 1e3)
+    e2e_value = world * K / (ms_e2e / 1e3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "size": 256, "batch_per_gpu": batch, "global_batch": batch * world,
+                   "parallelism": f"dp{world}", "conv_math": "tf32 (fp32 storage, fp32 accumulate)",
+                   "timing": "inputs regenerated on device every step (fresh latents/noise); activations + weights "
+                             "(~1.5 GB/iter) exceed L2",
+                   "fisher_rounds_in_timed": count(W, K, cfg.fisher_freq), "r1_iters_in_timed": count(W, K, 16),
+                   "path_iters_in_timed": count(W, K, 4)},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": batch * 3 * size * size * 4,
+                "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / K},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+
+    if rank == 0:
+        line["roofline"] = roofline_upfirdn2d(device)
+        line["extra"] = {"op_sweep": op_sweep(device), "fisher_round_ms": time_fisher_round(adapter, fisher_lat, shots_dev),
+                         "g_samples_per_s_b64_per_gpu": g_samples_per_s(Ge, device)}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(max_seconds=40.0)
+    if world > 1:
+        # sample generation scales by sharding batches with no communication: report the whole-job rate as well
+        sps = g_samples_per_s(Ge, device, batches=4)
+        t = torch.tensor([sps], device=device)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
+        if rank == 0:
+            line["extra"]["g_samples_per_s_b64_whole_job"] = float(t.item())
+        rdist.barrier()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def _flush_l2(buf):
+    buf.zero_()          # 256 MB write > 126 MB L2
+
+
+def _time_kernel(fn, flush_buf, iters=10, warm=3):
+    """average device time of fn() in ms: CUDA events on the launching stream, L2 flushed before every launch."""
+    for _ in range(warm):
+        fn()
+    times = []
+    for _ in range(iters):
+        _flush_l2(flush_buf)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        e.synchronize()
+        times.append(s.elapsed_time(e))
+    return sum(times) / len(times)
+
+
+def roofline_upfirdn2d(device):
+    """upfirdn2d (up=2, 4x4 blur), (32,512,128,128) -> (32,512,256,256) fp32: algorithmic bytes = 4*N*C*(HinWin+HoutWout)."""
+    from rick_b200 import op
+    peaks = load_peaks()
+    n, c, r = 32, 512, 128
+    x = torch.randn(n, c, r, r, device=device)
+    taps = torch.tensor([1., 3., 3., 1.], device=device)
+    taps = torch.outer(taps, taps) / 64 * 4
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    ms = _time_kernel(lambda: op.upfirdn2d(x, taps, up=2, pad=(2, 1)), flush)
+    bytes_alg = 4 * n * c * (r * r + 4 * r * r)
+    achieved = bytes_alg / (ms / 1e3) / 1e9
+    return {"kernel": "upfirdn2d_tiled<up=2>", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
+            "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+            "ms_per_launch": ms, "algorithmic_bytes": bytes_alg}
+
+
+def op_sweep(device):
+    """BASELINE configs[3]: achieved algorithmic GB/s of the memory-bound ops (fwd / bwd), fp32."""
+    from rick_b200 import op
+    out = {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    taps = torch.tensor([1., 3., 3., 1.], device=device)
+    taps4 = torch.outer(taps, taps) / 64 * 4
+    taps1 = torch.outer(taps, taps) / 64
+    n, c = 32, 512
+    for r in (16, 64, 128):
+        x = torch.randn(n, c, r, r, device=device)
+        ms = _time_kernel(lambda: op.upfirdn2d(x, taps4, up=2, pad=(2, 1)), flush, iters=5)
+        out[f"upfirdn2d_up2_{r}->{2 * r}"] = 4 * n * c * 5 * r * r / ms / 1e6
+        xb = torch.randn(n, c, 2 * r + 1, 2 * r + 1, device=device) if r <= 64 else None
+        if xb is not None:
+            ms = _time_kernel(lambda: op.upfirdn2d(xb, taps4, pad=(1, 1)), flush, iters=5)
+            out[f"blur_{2 * r + 1}->{2 * r}"] = 4 * n * c * ((2 * r + 1) ** 2 + 4 * r * r) / ms / 1e6
+            del xb
+        del x
+    x = torch.randn(n, c, 128, 128, device=device)
+    ms = _time_kernel(lambda: op.upfirdn2d(x, taps1, pad=(2, 2)), flush, iters=5)
+    out["d_blur_pad22_128->129"] = 4 * n * c * (128 * 128 + 129 * 129) / ms / 1e6
+    ms = _time_kernel(lambda: op.upfirdn2d(x, taps1, down=2, pad=(1, 1)), flush, iters=5)
+    out["down2_128->64"] = 4 * n * c * (128 * 128 + 64 * 64) / ms / 1e6
+    b = torch.randn(c, device=device)
+    for r in (16, 128):
+        xa = torch.randn(n, c, r, r, device=device)
+        ms = _time_kernel(lambda: op.fused_leaky_relu(xa, b), flush, iters=5)
+        out[f"bias_act_fwd_{r}"] = 4 * 2 * xa.numel() / ms / 1e6
+        xr = xa.clone().requires_grad_(True)
+        br = b.clone().requires_grad_(True)
+        y = op.fused_leaky_relu(xr, br)
+        go = torch.randn_like(y)
+        ms = _time_kernel(lambda: torch.autograd.grad(y, [xr, br], go, retain_graph=True), flush, iters=5)
+        out[f"bias_act_bwd_{r}"] = 4 * 3 * xa.numel() / ms / 1e6
+        del xa, xr, y, go
+    return {k: round(v, 1) for k, v in out.items()}
+
+
+def time_fisher_round(adapter, fisher_lat, shots_dev):
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    adapter.fisher_round(fisher_lat, shots_dev[:adapter.cfg.num_fisher_img])
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t) * 1e3
+
+
+@torch.no_grad()
+def g_samples_per_s(G, device, batches=6, batch=64):
+    from rick_b200.adapt import generate_samples
+    G.eval()
+    it = generate_samples(G, (batches + 2) * batch, batch, seed=1000)
+    next(it), next(it)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    n = 0
+    for _, img in it:
+        n += img.shape[0]
+    e.record()
+    e.synchronize()
+    return n / (s.elapsed_time(e) / 1e3)
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+
+def _oracle_adapter(threads):
+    from oracle import adapt_oracle as ao
+    from oracle import synth
+    from rick_b200.adapt import AdaptConfig, DrawStream
+    torch.set_num_threads(threads)
+    cfg = AdaptConfig(size=256, batch=2, warmup_iter=0, fisher_freq=50, num_fisher_img=5, fisher_quantile=40.0,
+                      prune_quantile=0.1)
+    gp, dp = synth.g_state(256, 1), synth.d_state(256, 2)
+    A = ao.OracleAdapter(cfg, gp, dp, {k: v.clone() for k, v in gp.items()}, {k: v.clone() for k, v in dp.items()})
+    return A, DrawStream(5, "cpu"), synth.shots(10, 256, 0)
+
+
+def cpu_baseline(max_seconds=40.0):
+    """Oracle port of ONE plain adaptation iteration (D step + G step, no regulariser, no Fisher round) on the host
+    cores of this box -- the reference's CPU path (upfirdn2d_native + native leaky-ReLU)."""
+    cores = len(os.sched_getaffinity(0))
+    A, draws, shots = _oracle_adapter(cores)
+    t = time.perf_counter()
+    A.step(1, shots[:2], draws, explicit_layer_noise=False)          # i = 1: no R1, no path-length
+    dt = time.perf_counter() - t
+    return {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"1 plain adaptation iteration (D step + G step, 256 px, batch 2), {dt:.1f} s, torch CPU "
+                      f"{torch.__version__}, {cores} threads"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port (the reference itself is
+    Python + JIT CUDA and cannot travel; its CPU branch is upfirdn2d_native, restated and pinned in oracle/)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    A, draws, shots = _oracle_adapter(cores)
+    W, K = args.warmup, args.steps
+    budget = 240.0
+    t0 = time.perf_counter()
+    A.step(1, shots[:2], draws, explicit_layer_noise=False)
+    first = time.perf_counter() - t0
+    # bounded sample: each step is one plain iteration; keep the whole run within a few minutes
+    k_run = max(1, min(K, int((budget - first) / max(first, 1e-3))))
+    w_run = 0 if k_run < K else max(0, min(W - 1, int((budget - first * (1 + k_run)) / max(first, 1e-3))))
+    for i in range(w_run):
+        A.step(1, shots[:2], draws, explicit_layer_noise=False)
+    t = time.perf_counter()
+    for i in range(k_run):
+        j = (2 * i) % 10
+        A.step(1 + 4 * i + 1, shots[j:j + 2], draws, explicit_layer_noise=False)   # indices that skip R1 / path-length
+    dt = time.perf_counter() - t
+    value = k_run / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+            "steps_run": k_run, "warmup": W, "warmup_run": w_run + 1, "ms_per_step": dt / k_run * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "size": 256, "batch_per_gpu": 2, "global_batch": 2,
+                       "parallelism": "cpu", "note": "plain iterations (D step + G step) of the oracle port on host "
+                                                     "cores; bounded sample"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{k_run} plain adaptation iterations, 256 px, batch 2, {cores} threads"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,128 @@
+/* rick_b200 -- C ABI of the B200-native RICK / StyleGAN2 hot path.
+ *
+ * Drop-in boundary.  Every entry point takes raw device pointers,
+ * explicit sizes, a dtype enum and a cudaStream_t (passed as void*), launches asynchronously
+ * on that stream, never allocates, never synchronises, and returns an int status
+ * (0 = RICK_OK).  No exceptions and no torch types cross this boundary.  All functions
+ * are re-entrant and keep no global mutable state; the device is the calling thread's
+ * current CUDA device (the Python shim sets it from the tensor).
+ *
+ * Reference interfaces replaced (paths relative to the reference tree):
+ *   rick_upfirdn2d            op/upfirdn2d.cpp:12-19  upfirdn2d(input, kernel, up_x, up_y, down_x, down_y,
+ *                             pad_x0, pad_x1, pad_y0, pad_y1) -> op/upfirdn2d_kernel.cu:209-369
+ *   rick_bias_act             op/fused_bias_act.cpp:11-17  fused_bias_act(input, bias, refer, act, grad, alpha, scale)
+ *                             -> op/fused_bias_act_kernel.cu:52-98
+ *   rick_bias_act_bwd         op/fused_act.py:19-39  (kernel mode act=3, grad=1) + the separate
+ *                             ``grad_input.sum(dim)`` bias reduction, fused into one pass
+ *   rick_fisher_*             train_dynamic_update_prune.py:252-269 (grad**2 accumulation / averaging on host NumPy)
+ *   rick_filter_fim           train:282, 291-293, 339-341, 349 (per-filter ``ndarray.mean`` [+ bias] / 2)
+ *   rick_percentile           train:285-286, 298-299, 352-353 (np.percentile, 'linear')
+ *   rick_decide               train:312-314, 324-330, 368-384 (np.where index sets) + 386-393 (cumulative prune union)
+ *   rick_mask_apply           train:427-437, 482-492, 521-539, 566-585 (index_put on param / grad per filter)
+ *   rick_modconv_*            gan_training/models/model_probe_tune.py:243-284 (ModulatedConv2d: modulate, demodulate,
+ *                             grouped conv / transposed conv) -- tcgen05 implicit GEMM, see rick_b200/csrc/conv_tc.cu
+ */
+#ifndef RICK_B200_H
+#define RICK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RICK_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define RICK_API __attribute__((visibility("default")))
+#else
+#define RICK_API
+#endif
+
+typedef void* rick_stream_t; /* cudaStream_t */
+
+enum rick_status {
+    RICK_OK = 0,
+    RICK_ERR_INVALID_ARGUMENT = 1, /* null pointer, non-positive size, bad enum */
+    RICK_ERR_UNSUPPORTED = 2,      /* valid request this build has no kernel for */
+    RICK_ERR_OVERFLOW = 3,         /* a size does not fit the kernel's index type */
+    RICK_ERR_CUDA = 4,             /* launch / runtime error, see rick_last_cuda_error() */
+    RICK_ERR_ALIGNMENT = 5         /* pointer not aligned for its element type */
+};
+
+enum rick_dtype { RICK_F32 = 0, RICK_BF16 = 1 };
+
+/* bias-act activation / derivative selectors, numbered as the reference kernel's (act, grad) pair */
+enum rick_act { RICK_ACT_LINEAR = 1, RICK_ACT_LRELU = 3 };
+
+RICK_API int rick_abi_version(void);
+RICK_API const char* rick_status_string(int status);
+/* cudaGetLastError()-style text of the most recent CUDA failure seen by the calling thread ("" if none) */
+RICK_API const char* rick_last_cuda_error(void);
+/* number of kernels launched by this library in this process so far (statistics for bench.py; monotonic) */
+RICK_API unsigned long long rick_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------- upfirdn2d
+ * in : (major, in_h, in_w, minor) contiguous     out: (major, out_h, out_w, minor) contiguous
+ * taps: (kh, kw) float32 on the device.  flip_taps != 0 uses taps[kh-1-i][kw-1-j] instead (what the
+ * reference obtains with torch.flip for the backward pass, op/upfirdn2d.py:101).
+ * out_h = (in_h*up_y + pad_y0 + pad_y1 - kh) / down_y + 1 (floor), same for w.
+ * minor == 1 is NCHW planes (major = N*C); minor == C is channels-last. */
+RICK_API int rick_upfirdn2d_out_size(int in_size, int k, int up, int down, int pad0, int pad1);
+RICK_API int rick_upfirdn2d(void* out, const void* in, const float* taps, int64_t major, int in_h, int in_w, int minor,
+                   int kh, int kw, int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0,
+                   int pad_y1, int flip_taps, int dtype, rick_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------- bias-act
+ * out[i] = f(x[i] + bias[(i / step_b) % size_b]) * scale with
+ *   act=LINEAR: f(v)=v;  act=LRELU, grad=0: v>0 ? v : v*alpha;  grad=1: ref[i]>0 ? v : v*alpha;  grad=2: 0.
+ * bias == NULL / ref == NULL mean "absent" (the reference passes empty tensors). */
+RICK_API int rick_bias_act(void* out, const void* x, const void* bias, const void* ref, int64_t n, int64_t step_b,
+                  int64_t size_b, int act, int grad, float alpha, float scale, int dtype, rick_stream_t stream);
+
+/* Fused backward of fused_leaky_relu: grad_in = (out>0 ? g : g*alpha)*scale and, in the same pass,
+ * grad_bias[c] = sum over (n, hw) of grad_in, deterministically (two-stage, no float atomics).
+ * Tensors are (N, C, HW) contiguous; grad_bias is float32 (C); workspace must hold
+ * rick_bias_act_bwd_workspace(N, C, HW) bytes. */
+RICK_API int64_t rick_bias_act_bwd_workspace(int64_t n, int64_t c, int64_t hw);
+RICK_API int rick_bias_act_bwd(void* grad_in, float* grad_bias, void* workspace, const void* grad_out, const void* out_saved,
+                      int64_t n, int64_t c, int64_t hw, float alpha, float scale, int dtype, rick_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------- Fisher
+ * acc/grad pointer tables are HOST arrays of DEVICE pointers (count entries); they are copied into kernel
+ * parameters, so no device-side table and no H2D copy is needed.
+ * first != 0:  acc = grad*grad       else:  acc = acc + grad*grad   (float32, product rounded before the add,
+ * exactly like ``fisher += (g ** 2).cpu().numpy()``). */
+RICK_API int rick_fisher_accum(float* const* acc, const float* const* grad, const int64_t* numel, int count, int first,
+                      rick_stream_t stream);
+/* acc[i] = acc[i] / divisor  (float32 division, ``fisher /= num_fisher_img * batch``) */
+RICK_API int rick_fisher_divide(float* const* acc, const int64_t* numel, int count, float divisor, rick_stream_t stream);
+
+/* Per-filter FIM of one layer: rows = filters, len = elements per filter (contiguous).
+ * fim[r] = mean_f32(fisher_w[r, :])                          if fisher_b == NULL
+ *        = (mean_f32(fisher_w[r, :]) + fisher_b[r]) / 2      otherwise
+ * mean_f32 reproduces NumPy's float32 pairwise summation order bit for bit. */
+RICK_API int rick_filter_fim(float* fim, const float* fisher_w, const float* fisher_b, int64_t rows, int64_t len,
+                    rick_stream_t stream);
+
+/* np.percentile(float64(fim[0:n]), q[j]) for j < nq (nq <= 8), method 'linear', by radix-select of the
+ * two neighbouring order statistics; q is a HOST array; lines is a DEVICE array of nq doubles. */
+RICK_API int rick_percentile(double* lines, const float* fim, int64_t n, const double* q, int nq, rick_stream_t stream);
+
+/* state[i] = (fim>cut ? 1:0) | (prune ? 2:0) | (fine-tune ? 4:0) with cut = lines[0], pruneline = lines[1];
+ * closed_low selects the reference's D-skip comparisons (train:382-384).  If zero_mask != NULL it is OR-ed
+ * with the prune bit (cumulative prune set, train:386-393); pass reset_zero != 0 on the first round. */
+RICK_API int rick_decide(uint8_t* state, uint8_t* zero_mask, const float* fim, int64_t n, const double* lines,
+                int closed_low, int reset_zero, rick_stream_t stream);
+
+/* One launch for a whole model.  Entry t: param/grad are (rows[t], inner[t]) contiguous float32, state / zero are
+ * per-row bytes (NULL = no such set for this tensor).  grad rows with (state&1) or zero are cleared, param rows
+ * with zero are cleared.  Tables are HOST arrays. */
+RICK_API int rick_mask_apply(float* const* param, float* const* grad, const uint8_t* const* state,
+                    const uint8_t* const* zero, const int64_t* rows, const int64_t* inner, int count,
+                    rick_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RICK_B200_H */

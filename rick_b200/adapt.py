@@ -1,0 +1,299 @@
+"""The RICK adaptation iteration and FID-style sample generation on top of the sm_100a hot path.
+
+Host-side mirror of the reference's ``train()`` loop body (train_dynamic_update_prune.py:193-699) and of the sample
+loop of ``Evaluator.compute_inception_score`` (gan_training/eval.py:31-46), restructured so that the device is never
+idle waiting for the host:
+
+  * Fisher tensors, FIM vectors, thresholds and masks stay on the GPU (rick_b200/rick.py); the reference round-trips
+    ~235 MB per Fisher image through NumPy and re-uploads index arrays every iteration.
+  * No ``.item()`` / ``empty_cache()`` inside the iteration (the reference has ten such syncs, e.g. train:425, 596-603).
+  * The D step runs G under ``no_grad`` and the G step differentiates only w.r.t. G's parameters.  Both are
+    result-preserving: the reference back-propagates into the other network and then discards those gradients with
+    ``zero_grad()`` (train:401-420, 516).
+  * Optimiser selection, betas, warm-up gating, regulariser schedule, EMA and the order in which random numbers are
+    consumed are the reference's.
+
+All randomness comes from a ``DrawStream`` so that a seeded CPU oracle run can consume the identical sequence
+(tests/test_adapt_parity.py); for throughput runs the stream draws on the device.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+from torch import autograd, optim
+from torch.nn import functional as F
+
+from . import dist as rdist
+from . import rick
+
+
+@dataclass
+class AdaptConfig:
+    size: int = 256
+    batch: int = 2
+    latent: int = 512
+    n_mlp: int = 8
+    channel_multiplier: int = 2
+    lr: float = 0.002
+    r1: float = 10.0
+    path_regularize: float = 2.0
+    path_batch_shrink: int = 2
+    d_reg_every: int = 16
+    g_reg_every: int = 4
+    mixing: float = 0.9
+    warmup_iter: int = 0
+    fisher_freq: int = 50
+    num_fisher_img: int = 5
+    fisher_quantile: float = 40.0
+    prune_quantile: float = 0.1
+
+
+class DrawStream:
+    """Every random quantity one adaptation run consumes, in the reference's order.
+
+    ``cpu_seeded=True`` draws from a seeded CPU generator and moves the result to ``device`` (bit-identical across
+    machines: this is what parity tests use on both the CUDA path and the CPU oracle).  ``cpu_seeded=False`` draws on
+    the device (throughput runs)."""
+
+    def __init__(self, seed: int, device, cpu_seeded: bool = True):
+        self.device = torch.device(device)
+        self.cpu_seeded = cpu_seeded
+        self.gen = torch.Generator(device="cpu" if cpu_seeded else self.device).manual_seed(seed)
+
+    def normal(self, *shape) -> torch.Tensor:
+        if self.cpu_seeded:
+            return torch.randn(*shape, generator=self.gen).to(self.device, non_blocking=True)
+        return torch.randn(*shape, generator=self.gen, device=self.device)
+
+    def uniform(self) -> float:
+        g = self.gen if self.cpu_seeded else None
+        return float(torch.rand(1, generator=g))
+
+    def randint(self, lo: int, hi: int) -> int:
+        """inclusive bounds, like ``random.randint`` (model_probe_tune.py:556)"""
+        g = self.gen if self.cpu_seeded else None
+        return int(torch.randint(lo, hi + 1, (1,), generator=g))
+
+    # ---- composite draws ----
+    def mixing_latents(self, batch: int, latent: int, prob: float) -> List[torch.Tensor]:
+        """mixing_noise (train:130-135)"""
+        if prob > 0 and self.uniform() < prob:
+            z = self.normal(2, batch, latent)
+            return [z[0], z[1]]
+        return [self.normal(batch, latent)]
+
+    def layer_noise(self, batch: int, size: int) -> List[torch.Tensor]:
+        """per-layer NoiseInjection draws in forward order (model_probe_tune.py:294-296)"""
+        log_size = int(math.log2(size))
+        out = [self.normal(batch, 1, 4, 4)]
+        for i in range(3, log_size + 1):
+            out += [self.normal(batch, 1, 2 ** i, 2 ** i), self.normal(batch, 1, 2 ** i, 2 ** i)]
+        return out
+
+
+def d_logistic_loss(real_pred, fake_pred):
+    return F.softplus(-real_pred).mean() + F.softplus(fake_pred).mean()
+
+
+def g_nonsaturating_loss(fake_pred):
+    return F.softplus(-fake_pred).mean()
+
+
+def d_r1_loss(real_pred, real_img):
+    (grad_real,) = autograd.grad(outputs=real_pred.sum(), inputs=real_img, create_graph=True)
+    return grad_real.pow(2).reshape(grad_real.shape[0], -1).sum(1).mean()
+
+
+def g_path_regularize(fake_img, latents, mean_path_length, noise, decay=0.01):
+    noise = noise / math.sqrt(fake_img.shape[2] * fake_img.shape[3])
+    (grad,) = autograd.grad(outputs=(fake_img * noise).sum(), inputs=latents, create_graph=True)
+    path_lengths = torch.sqrt(grad.pow(2).sum(2).mean(1))
+    path_mean = mean_path_length + decay * (path_lengths.mean() - mean_path_length)
+    path_penalty = (path_lengths - path_mean).pow(2).mean()
+    return path_penalty, path_mean.detach(), path_lengths
+
+
+class RickAdapter:
+    """Owns the four networks, the two Adam optimisers, the Fisher accumulators and the filter masks."""
+
+    def __init__(self, cfg: AdaptConfig, generator, discriminator, g_ema, d_ema, fused_adam: bool = True):
+        self.cfg = cfg
+        self.g, self.d, self.g_ema, self.d_ema = generator, discriminator, g_ema, d_ema
+        self.device = next(generator.parameters()).device
+        g_ratio = cfg.g_reg_every / (cfg.g_reg_every + 1)
+        d_ratio = cfg.d_reg_every / (cfg.d_reg_every + 1)
+        self.g_named = dict(generator.named_parameters())
+        self.d_named = dict(discriminator.named_parameters())
+        # trainable subsets, train:908-931
+        self.g_train = [p for n, p in self.g_named.items() if "convs" in n]
+        self.d_train = [p for n, p in self.d_named.items()
+                        if ("convs" in n and "convs.0" not in n) or "final" in n]
+        kw = dict(fused=True) if fused_adam and self.device.type == "cuda" else {}
+        self.g_optim = optim.Adam(self.g_train, lr=cfg.lr * g_ratio, betas=(0 ** g_ratio, 0.99 ** g_ratio), **kw)
+        self.d_optim = optim.Adam(self.d_train, lr=cfg.lr * d_ratio, betas=(0 ** d_ratio, 0.99 ** d_ratio), **kw)
+        self.acc_g = rick.FisherAccumulator(g_ema.named_parameters())
+        self.acc_d = rick.FisherAccumulator(d_ema.named_parameters())
+        self.masks_g = rick.FilterMasks(rick.generator_layers(dict(g_ema.named_parameters())), self.device)
+        self.masks_d = rick.FilterMasks(rick.discriminator_layers(dict(d_ema.named_parameters())), self.device)
+        self.mean_path_length = torch.zeros((), device=self.device)
+        self.ema_decay = 0.5 ** (32 / (10 * 1000))
+        self._ema_pairs = None
+
+    # ------------------------------------------------------------------------------------------ Fisher round
+    def fisher_round(self, latents: torch.Tensor, reals: torch.Tensor, layer_noise: Optional[list] = None):
+        """train:214-393.  ``latents`` (num_fisher_img, latent) are the reference's ``_noise/000j.pt`` rows,
+        ``reals`` (num_fisher_img, 3, H, W) the first image of each loader batch."""
+        cfg = self.cfg
+        for m in (self.g_ema, self.d_ema):
+            for p in m.parameters():
+                p.requires_grad_(True)
+            m.eval()
+        self.acc_g.reset()
+        self.acc_d.reset()
+        g_params = list(self.g_ema.parameters())
+        d_params = list(self.d_ema.parameters())
+        world = rdist.world_size()
+        rank = torch.distributed.get_rank() if world > 1 else 0
+        mine = rdist.shard_range(latents.shape[0], rank, world)     # Fisher images are sharded over ranks
+        for j in mine:
+            noise = None if layer_noise is None else layer_noise[j]
+            fake, _ = self.g_ema([latents[j:j + 1]], noise=noise)
+            fake_pred, _ = self.d_ema(fake)
+            real_pred, _ = self.d_ema(reals[j:j + 1])
+            g_loss = g_nonsaturating_loss(fake_pred)
+            d_loss = d_logistic_loss(real_pred, fake_pred)
+            g_grads = autograd.grad(g_loss, g_params, retain_graph=True)
+            d_grads = autograd.grad(d_loss, d_params)
+            self.acc_g.add(g_grads)
+            self.acc_d.add(d_grads)
+        if world > 1:                                  # one exchange step: SUM of the grad^2 accumulators
+            for acc in (self.acc_g, self.acc_d):
+                if acc.count == 0:
+                    for t in acc.acc:
+                        t.zero_()
+                rdist.allreduce_sum_(acc.acc)
+        div = cfg.num_fisher_img * cfg.batch          # the reference's divisor (train:267), kept as is
+        self.acc_g.average(div)
+        self.acc_d.average(div)
+        self.masks_g.update(self.acc_g.as_dict(), cfg.fisher_quantile, cfg.prune_quantile)
+        self.masks_d.update(self.acc_d.as_dict(), cfg.fisher_quantile, cfg.prune_quantile)
+
+    # ------------------------------------------------------------------------------------------ one iteration
+    def _gate_warmup(self, i: int):
+        warm = i < self.cfg.warmup_iter
+        for n, p in self.d_named.items():
+            p.requires_grad_((not warm) or ("final" in n))
+
+    def step(self, i: int, real_img: torch.Tensor, draws: DrawStream, explicit_layer_noise: bool = False
+             ) -> Dict[str, torch.Tensor]:
+        """One iteration of train:396-589 + EMA (697-698).  Returns loss tensors (no host sync)."""
+        cfg = self.cfg
+        after_warmup = i >= cfg.warmup_iter
+        self._gate_warmup(i)
+        noise_of = (lambda b: draws.layer_noise(b, cfg.size)) if explicit_layer_noise else (lambda b: None)
+        out: Dict[str, torch.Tensor] = {}
+
+        # ---- D step (train:396-438) ----
+        z = draws.mixing_latents(cfg.batch, cfg.latent, cfg.mixing)
+        inject = draws.randint(1, self.g.n_latent - 1) if len(z) == 2 else None
+        with torch.no_grad():
+            fake_img, _ = self.g(z, inject_index=inject, noise=noise_of(cfg.batch))
+        fake_pred, _ = self.d(fake_img)
+        real_pred, _ = self.d(real_img)
+        d_loss = d_logistic_loss(real_pred, fake_pred)
+        out["d"], out["real_score"], out["fake_score"] = d_loss.detach(), real_pred.mean().detach(), fake_pred.mean().detach()
+        self.d.zero_grad(set_to_none=True)
+        d_loss.backward()
+        self._sync_grads(self.d_train)
+        if after_warmup:
+            self.masks_d.apply(self.d_named)
+        self.d_optim.step()
+
+        # ---- R1 (train:462-493) ----
+        if i % cfg.d_reg_every == 0:
+            real_r = real_img.detach().requires_grad_(True)
+            real_pred, _ = self.d(real_r)
+            real_pred = real_pred.view(real_r.size(0), -1).mean(dim=1).unsqueeze(1)
+            r1_loss = d_r1_loss(real_pred, real_r)
+            self.d.zero_grad(set_to_none=True)
+            (cfg.r1 / 2 * r1_loss * cfg.d_reg_every + 0 * real_pred[0]).backward()
+            self._sync_grads(self.d_train)
+            if after_warmup:
+                self.masks_d.apply(self.d_named)
+            self.d_optim.step()
+            out["r1"] = r1_loss.detach()
+
+        # ---- G step (train:500-540) ----
+        z = draws.mixing_latents(cfg.batch, cfg.latent, cfg.mixing)
+        inject = draws.randint(1, self.g.n_latent - 1) if len(z) == 2 else None
+        if after_warmup:
+            fake_img, _ = self.g(z, inject_index=inject, noise=noise_of(cfg.batch))
+            fake_pred, _ = self.d(fake_img)
+            g_loss = g_nonsaturating_loss(fake_pred)
+            self.g.zero_grad(set_to_none=True)
+            autograd.backward(g_loss, inputs=self.g_train)
+            self._sync_grads(self.g_train)
+            self.masks_g.apply(self.g_named)
+            self.g_optim.step()
+        else:
+            with torch.no_grad():                       # warm-up: the loss is only logged (train:518-519)
+                fake_img, _ = self.g(z, inject_index=inject, noise=noise_of(cfg.batch))
+                g_loss = g_nonsaturating_loss(self.d(fake_img)[0])
+        out["g"] = g_loss.detach()
+
+        # ---- path-length regularisation (train:546-589) ----
+        if i % cfg.g_reg_every == 0 and after_warmup:
+            pb = max(1, cfg.batch // cfg.path_batch_shrink)
+            z = draws.mixing_latents(pb, cfg.latent, cfg.mixing)
+            inject = draws.randint(1, self.g.n_latent - 1) if len(z) == 2 else None
+            fake_img, latents = self.g(z, return_latents=True, inject_index=inject, noise=noise_of(pb))
+            path_loss, self.mean_path_length, path_lengths = g_path_regularize(
+                fake_img, latents, self.mean_path_length, draws.normal(*fake_img.shape))
+            self.g.zero_grad(set_to_none=True)
+            weighted = cfg.path_regularize * cfg.g_reg_every * path_loss
+            if cfg.path_batch_shrink:
+                weighted = weighted + 0 * fake_img[0, 0, 0, 0]
+            autograd.backward(weighted, inputs=self.g_train)
+            self._sync_grads(self.g_train)
+            self.masks_g.apply(self.g_named)
+            self.g_optim.step()
+            out["path"], out["path_length"] = path_loss.detach(), path_lengths.mean().detach()
+
+        # ---- EMA (train:697-698) ----
+        self._ema()
+        return out
+
+    @staticmethod
+    def _sync_grads(params):
+        """DDP exchange step: average the gradients over ranks (no-op in a single process)."""
+        if rdist.world_size() > 1:
+            rdist.allreduce_mean_([p.grad for p in params if p.grad is not None])
+
+    @torch.no_grad()
+    def _ema(self):
+        if self._ema_pairs is None:
+            ge, gs = dict(self.g_ema.named_parameters()), self.g_named
+            de, ds = dict(self.d_ema.named_parameters()), self.d_named
+            self._ema_pairs = ([ge[k] for k in ge] + [de[k] for k in de], [gs[k] for k in ge] + [ds[k] for k in de])
+        dst, src = self._ema_pairs
+        torch._foreach_mul_(dst, self.ema_decay)
+        torch._foreach_add_(dst, src, alpha=1 - self.ema_decay)
+
+
+@torch.no_grad()
+def generate_samples(generator, n_samples: int, batch: int, latent: int = 512, rank: int = 0, world: int = 1,
+                     seed: int = 0, to_host: bool = False):
+    """Batch-sharded sample generation (gan_training/eval.py:31-46): rank r takes batches
+    r, r+W, ...; ``z`` for batch k comes from ``manual_seed(seed + k)`` so any sharding produces the same images.
+    Yields (batch_index, images)."""
+    device = next(generator.parameters()).device
+    n_batches = (n_samples + batch - 1) // batch
+    gen = torch.Generator(device=device)
+    for k in range(rank, n_batches, world):
+        gen.manual_seed(seed + k)
+        z = torch.randn(batch, latent, generator=gen, device=device)
+        img, _ = generator([z])
+        yield k, (img.cpu() if to_host else img)

@@ -1,0 +1,54 @@
+"""Convolution dispatch for the StyleGAN2 stack.
+
+Two executors sit behind ``modulated_conv2d`` / ``conv2d``:
+
+  * ``tc``     the hand-written tcgen05 / TMEM / TMA implicit-GEMM kernels of this package
+               (rick_b200/csrc/conv_tc.cu via the C ABI) -- TF32 operands, fp32 accumulation in tensor memory,
+               demodulation + noise + bias + leaky-ReLU fused into the epilogue.  Used wherever it is implemented
+               (see ``tc_supported``); the status table lives in DESIGN.md.
+  * ``cudnn``  ATen / cuDNN dense convolutions on the SHARED weight (``groups = 1``: the modulation is folded into
+               the activations and the demodulation into the output, so this is a plain library conv, not the
+               reference's grouped conv on materialised per-sample weights).  It is the differentiable path
+               (first and second derivatives for R1 / path-length) until the tcgen05 dgrad / wgrad kernels land.
+
+There is no CPU executor: inputs must be CUDA tensors.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+from torch.nn import functional as F
+
+_FORCE = os.environ.get("RICK_CONV_BACKEND", "")   # "", "cudnn" or "tc" (tests use it to pin an executor)
+
+
+def _require_cuda(x: torch.Tensor, what: str):
+    if not x.is_cuda:
+        raise RuntimeError(f"rick_b200.conv.{what}: input must be a CUDA tensor (no CPU fallback in this package)")
+
+
+def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], stride: int = 1, padding: int = 0):
+    """EqualConv2d's dense convolution (model_probe_tune.py:121-130)."""
+    _require_cuda(x, "conv2d")
+    return F.conv2d(x, weight, bias=bias, stride=stride, padding=padding)
+
+
+def modulated_conv2d(x: torch.Tensor, w: torch.Tensor, s: torch.Tensor, demod: Optional[torch.Tensor],
+                     upsample: bool = False, downsample: bool = False, padding: int = 1, blur=None) -> torch.Tensor:
+    """out[b] = demod[b] * conv(x[b] * s[b], w)  -- ModulatedConv2d (model_probe_tune.py:243-284) without
+    per-sample weights.  ``w`` is the shared (Cout, Cin, k, k) weight already multiplied by the equalised-lr scale,
+    ``s`` the (B, Cin) style, ``demod`` the (B, Cout) demodulation or None."""
+    _require_cuda(x, "modulated_conv2d")
+    xm = x * s[:, :, None, None]
+    if upsample:
+        out = F.conv_transpose2d(xm, w.transpose(0, 1), stride=2, padding=0)
+        out = blur(out)
+    elif downsample:
+        out = F.conv2d(blur(xm), w, stride=2, padding=0)
+    else:
+        out = F.conv2d(xm, w, padding=padding)
+    if demod is not None:
+        out = out * demod[:, :, None, None]
+    return out

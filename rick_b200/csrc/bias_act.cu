@@ -1,0 +1,257 @@
+// Fused bias + leaky-ReLU * scale for sm_100a: forward, first derivative (with the per-channel bias-gradient
+// reduction fused into the same pass) and second derivative.
+//
+// Replaces op/fused_bias_act_kernel.cu (fused_bias_act_op, :52-98) behind the same native signature
+// (op/fused_bias_act.cpp:11-17), plus the ``grad_input.sum(dim)`` ATen reduction that op/fused_act.py:31-37 runs as
+// a second full read of grad_input.  HBM-bound: forward moves 2 elements per output (read x, write out), the fused
+// backward 3 (read grad_out, read saved out, write grad_in).
+//
+// Layout: flat contiguous tensor; the bias channel of element i is (i / step_b) % size_b with step_b = prod(dims[2:]).
+// Vector path: 128-bit streaming loads/stores, one integer divide per 16 bytes (all lanes of a vector share a
+// channel because step_b is a multiple of the vector width); 64-bit element indices.
+#include "common.cuh"
+
+namespace rick {
+
+template <typename T> struct Vec16;  // 16 bytes of T <-> fp32 lanes
+template <> struct Vec16<float> {
+    static constexpr int N = 4;
+    static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+        float4 t = ld_stream_f4(reinterpret_cast<const float4*>(p));
+        v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+        st_stream_f4(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+    }
+};
+template <> struct Vec16<__nv_bfloat16> {
+    static constexpr int N = 8;
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+        uint4 t = ld_stream_u4(reinterpret_cast<const uint4*>(p));
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[2 * i] = __uint_as_float(w[i] << 16);
+            v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        st_stream_u4(reinterpret_cast<uint4*>(p), make_uint4(w[0], w[1], w[2], w[3]));
+    }
+};
+
+__device__ __forceinline__ float act_apply(float v, float gate, int act, int grad, float alpha) {
+    if (grad == 2) return 0.f;
+    if (act == RICK_ACT_LRELU) return gate > 0.f ? v : v * alpha;
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------ forward / generic modes
+template <typename T>
+__global__ void __launch_bounds__(256) bias_act_vec(T* __restrict__ out, const T* __restrict__ x,
+                                                    const T* __restrict__ bias, const T* __restrict__ ref,
+                                                    long long nvec, long long step_vec, int size_b, int act, int grad,
+                                                    float alpha, float scale) {
+    constexpr int N = Vec16<T>::N;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        float v[N], r[N];
+        Vec16<T>::load(x + i * N, v);
+        if (ref) Vec16<T>::load(ref + i * N, r);
+        float b = 0.f;
+        if (bias) b = Elem<T>::ld(bias + (int)((i / step_vec) % size_b));
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            const float t = v[k] + b;
+            v[k] = act_apply(t, (grad == 0) ? t : (ref ? r[k] : 0.f), act, grad, alpha) * scale;
+        }
+        Vec16<T>::store(out + i * N, v);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bias_act_scalar(T* __restrict__ out, const T* __restrict__ x,
+                                                       const T* __restrict__ bias, const T* __restrict__ ref,
+                                                       long long n, long long step_b, int size_b, int act, int grad,
+                                                       float alpha, float scale) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+        float t = Elem<T>::ld(x + i);
+        if (bias) t += Elem<T>::ld(bias + (int)((i / step_b) % size_b));
+        const float gate = (grad == 0) ? t : (ref ? Elem<T>::ld(ref + i) : 0.f);
+        Elem<T>::st(out + i, act_apply(t, gate, act, grad, alpha) * scale);
+    }
+}
+
+template <typename T>
+static int launch_bias_act(void* out, const void* x, const void* bias, const void* ref, int64_t n, int64_t step_b,
+                           int64_t size_b, int act, int grad, float alpha, float scale, cudaStream_t s) {
+    constexpr int N = Vec16<T>::N;
+    const bool vec = (n % N == 0) && (!bias || step_b % N == 0) && aligned_to(out, 16) && aligned_to(x, 16) &&
+                     (!ref || aligned_to(ref, 16));
+    const long long cap = (long long)kNumSMs * 16;
+    if (vec) {
+        const long long nvec = n / N;
+        long long blocks = ceil_div(nvec, 256);
+        if (blocks > cap) blocks = cap;
+        bias_act_vec<T><<<(unsigned)blocks, 256, 0, s>>>((T*)out, (const T*)x, (const T*)bias, (const T*)ref, nvec,
+                                                          bias ? step_b / N : 1, (int)size_b, act, grad, alpha, scale);
+    } else {
+        long long blocks = ceil_div(n, 256);
+        if (blocks > cap) blocks = cap;
+        bias_act_scalar<T><<<(unsigned)blocks, 256, 0, s>>>((T*)out, (const T*)x, (const T*)bias, (const T*)ref, n,
+                                                             bias ? step_b : 1, (int)size_b, act, grad, alpha, scale);
+    }
+    RICK_CHECK_LAUNCH();
+    return RICK_OK;
+}
+
+// ------------------------------------------------------------------------------------------ fused backward
+// A warp owns one (plane, chunk) work item: chunk = 32 lanes x UNR vectors.  Partial sums go to
+// workspace[plane * chunks + chunk]; a second small kernel folds them per channel in a fixed order.
+constexpr int kBwdUnroll = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(256) bias_act_bwd_main(T* __restrict__ gin, float* __restrict__ partial,
+                                                         const T* __restrict__ gout, const T* __restrict__ saved,
+                                                         long long planes, long long hw_vec, int chunks, float alpha,
+                                                         float scale) {
+    constexpr int N = Vec16<T>::N;
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long items = planes * chunks;
+    for (long long item = warp0; item < items; item += nwarps) {
+        const long long plane = item / chunks;
+        const int chunk = (int)(item - plane * chunks);
+        const long long base = plane * hw_vec;
+        const long long v0 = (long long)chunk * (32 * kBwdUnroll);
+        float g[kBwdUnroll][N], o[kBwdUnroll][N];
+        bool ok[kBwdUnroll];
+#pragma unroll
+        for (int u = 0; u < kBwdUnroll; ++u) {
+            const long long vi = v0 + u * 32 + lane;
+            ok[u] = vi < hw_vec;
+            if (ok[u]) {
+                Vec16<T>::load(gout + (base + vi) * N, g[u]);
+                Vec16<T>::load(saved + (base + vi) * N, o[u]);
+            }
+        }
+        float acc = 0.f;
+#pragma unroll
+        for (int u = 0; u < kBwdUnroll; ++u) {
+            if (!ok[u]) continue;
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                g[u][k] = (o[u][k] > 0.f ? g[u][k] : g[u][k] * alpha) * scale;
+                acc += g[u][k];
+            }
+            Vec16<T>::store(gin + (base + v0 + u * 32 + lane) * N, g[u]);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) partial[item] = acc;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bias_act_bwd_scalar(T* __restrict__ gin, const T* __restrict__ gout,
+                                                           const T* __restrict__ saved, long long n, float alpha,
+                                                           float scale) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float g = Elem<T>::ld(gout + i);
+        Elem<T>::st(gin + i, (Elem<T>::ld(saved + i) > 0.f ? g : g * alpha) * scale);
+    }
+}
+
+// grad_bias[c] = sum_n sum_j src[(n*C + c) * len + j]; one warp per channel, fixed order -> deterministic
+template <typename S>
+__global__ void __launch_bounds__(256) bias_grad_fold(float* __restrict__ grad_bias, const S* __restrict__ src,
+                                                      int n, int c, long long len) {
+    const int lane = threadIdx.x & 31;
+    const int ch = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+    if (ch >= c) return;
+    float acc = 0.f;
+    for (int b = 0; b < n; ++b) {
+        const S* row = src + ((long long)b * c + ch) * len;
+        for (long long j = lane; j < len; j += 32) acc += Elem<S>::ld(row + j);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) grad_bias[ch] = acc;
+}
+
+static inline int bwd_chunks(int64_t hw_vec) { return (int)ceil_div(hw_vec, 32 * kBwdUnroll); }
+
+template <typename T>
+static int launch_bias_act_bwd(void* gin, float* grad_bias, void* ws, const void* gout, const void* saved, int64_t n,
+                               int64_t c, int64_t hw, float alpha, float scale, cudaStream_t s) {
+    constexpr int N = Vec16<T>::N;
+    const bool vec = (hw % N == 0) && aligned_to(gin, 16) && aligned_to(gout, 16) && aligned_to(saved, 16);
+    const long long cap = (long long)kNumSMs * 16;
+    const unsigned fold_blocks = (unsigned)ceil_div(c * 32, 256);
+    if (vec) {
+        const int64_t hw_vec = hw / N;
+        const int chunks = bwd_chunks(hw_vec);
+        const long long items = n * c * chunks;
+        long long blocks = ceil_div(items, 8);
+        if (blocks > cap) blocks = cap;
+        bias_act_bwd_main<T><<<(unsigned)blocks, 256, 0, s>>>((T*)gin, (float*)ws, (const T*)gout, (const T*)saved,
+                                                               n * c, hw_vec, chunks, alpha, scale);
+        RICK_CHECK_LAUNCH();
+        bias_grad_fold<float><<<fold_blocks, 256, 0, s>>>(grad_bias, (const float*)ws, (int)n, (int)c, chunks);
+    } else {
+        const long long total = n * c * hw;
+        long long blocks = ceil_div(total, 256);
+        if (blocks > cap) blocks = cap;
+        bias_act_bwd_scalar<T><<<(unsigned)blocks, 256, 0, s>>>((T*)gin, (const T*)gout, (const T*)saved, total, alpha,
+                                                                 scale);
+        RICK_CHECK_LAUNCH();
+        bias_grad_fold<T><<<fold_blocks, 256, 0, s>>>(grad_bias, (const T*)gin, (int)n, (int)c, hw);
+    }
+    RICK_CHECK_LAUNCH();
+    return RICK_OK;
+}
+
+}  // namespace rick
+
+extern "C" int rick_bias_act(void* out, const void* x, const void* bias, const void* ref, int64_t n, int64_t step_b,
+                             int64_t size_b, int act, int grad, float alpha, float scale, int dtype,
+                             rick_stream_t stream) {
+    using namespace rick;
+    if (!out || !x || n < 0) return RICK_ERR_INVALID_ARGUMENT;
+    if (act != RICK_ACT_LINEAR && act != RICK_ACT_LRELU) return RICK_ERR_UNSUPPORTED;
+    if (grad < 0 || grad > 2) return RICK_ERR_INVALID_ARGUMENT;
+    if (bias && (step_b < 1 || size_b < 1 || size_b > 0x7fffffff)) return RICK_ERR_INVALID_ARGUMENT;
+    if (dtype != RICK_F32 && dtype != RICK_BF16) return RICK_ERR_INVALID_ARGUMENT;
+    if (n == 0) return RICK_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == RICK_F32)
+        return launch_bias_act<float>(out, x, bias, ref, n, step_b, size_b, act, grad, alpha, scale, s);
+    return launch_bias_act<__nv_bfloat16>(out, x, bias, ref, n, step_b, size_b, act, grad, alpha, scale, s);
+}
+
+extern "C" int64_t rick_bias_act_bwd_workspace(int64_t n, int64_t c, int64_t hw) {
+    if (n < 1 || c < 1 || hw < 1) return 0;
+    // sized for the widest case (fp32 vectors of 4): n*c*chunks floats
+    return n * c * (int64_t)rick::bwd_chunks(rick::ceil_div(hw, 4)) * (int64_t)sizeof(float);
+}
+
+extern "C" int rick_bias_act_bwd(void* grad_in, float* grad_bias, void* workspace, const void* grad_out,
+                                 const void* out_saved, int64_t n, int64_t c, int64_t hw, float alpha, float scale,
+                                 int dtype, rick_stream_t stream) {
+    using namespace rick;
+    if (!grad_in || !grad_bias || !grad_out || !out_saved || !workspace) return RICK_ERR_INVALID_ARGUMENT;
+    if (n < 1 || c < 1 || hw < 1 || c > 0x7fffffff || n > 0x7fffffff) return RICK_ERR_INVALID_ARGUMENT;
+    if (dtype != RICK_F32 && dtype != RICK_BF16) return RICK_ERR_INVALID_ARGUMENT;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == RICK_F32)
+        return launch_bias_act_bwd<float>(grad_in, grad_bias, workspace, grad_out, out_saved, n, c, hw, alpha, scale, s);
+    return launch_bias_act_bwd<__nv_bfloat16>(grad_in, grad_bias, workspace, grad_out, out_saved, n, c, hw, alpha,
+                                              scale, s);
+}

@@ -1,0 +1,389 @@
+"""StyleGAN2 generator / discriminator modules with the reference's names, constructor signatures, return tuples
+and state_dict keys (gan_training/models/model_probe_tune.py), so reference checkpoints load unchanged and the
+Fisher step's string keys (train_dynamic_update_prune.py:282-351) resolve.
+
+What is different underneath:
+  * ``upfirdn2d`` / ``fused_leaky_relu`` are the sm_100a kernels of this package (rick_b200/op).
+  * ``ModulatedConv2d`` never materialises per-sample weights.  It uses the algebraic form
+        out[b] = demod[b, :, None, None] * conv(x[b] * s[b, :, None, None], scale * W)
+        demod[b, co] = rsqrt( sum_ci s[b, ci]^2 * sum_{kh,kw} (scale * W[co, ci])^2 + 1e-8 )
+    (identical to model_probe_tune.py:246-251 up to float rounding), so the batch folds into one dense convolution
+    on the shared weight instead of ``groups = batch`` convolutions on B x 9.4 MB of weights.
+  * ``Discriminator.forward`` does not evaluate conv1 / conv2 of every block twice; the reference does so only to
+    fill a ``feat`` list the trainer throws away (model_probe_tune.py:740-744, train:407-410).  ``feat`` is still
+    returned, filled from the single evaluation.
+The dense convolutions themselves go through ``rick_b200.conv`` (tcgen05 implicit GEMM where available, see
+DESIGN.md for the per-path status).
+"""
+from __future__ import annotations
+
+import math
+import random
+from typing import List, Optional
+
+import torch
+from torch import autograd, nn
+from torch.nn import functional as F
+
+from . import conv as _conv
+from .op import FusedLeakyReLU, fused_leaky_relu, upfirdn2d
+
+
+def make_kernel(k):
+    k = torch.as_tensor(k, dtype=torch.float32)
+    if k.dim() == 1:
+        k = torch.outer(k, k)
+    return k / k.sum()
+
+
+def _fir_pads(taps: int, factor: int, kernel_size: int, mode: str):
+    """Padding arithmetic of Upsample / Downsample / Blur-around-conv (model_probe_tune.py:48-53, 69-74, 209-223, 608-612)."""
+    if mode == "up":        # Upsample module
+        p = taps - factor
+        return (p + 1) // 2 + factor - 1, p // 2
+    if mode == "down":      # Downsample module
+        p = taps - factor
+        return (p + 1) // 2, p // 2
+    if mode == "conv_up":   # blur after a stride-2 transposed conv
+        p = (taps - factor) - (kernel_size - 1)
+        return (p + 1) // 2 + factor - 1, p // 2 + 1
+    p = (taps - factor) + (kernel_size - 1)   # "conv_down": blur before a stride-2 conv
+    return (p + 1) // 2, p // 2
+
+
+class PixelNorm(nn.Module):
+    def forward(self, input):
+        return input * torch.rsqrt(torch.mean(input ** 2, dim=1, keepdim=True) + 1e-8)
+
+
+class Upsample(nn.Module):
+    def __init__(self, kernel, factor=2):
+        super().__init__()
+        self.factor = factor
+        self.register_buffer("kernel", make_kernel(kernel) * (factor ** 2))
+        self.pad = _fir_pads(self.kernel.shape[0], factor, 1, "up")
+
+    def forward(self, input):
+        return upfirdn2d(input, self.kernel, up=self.factor, down=1, pad=self.pad)
+
+
+class Downsample(nn.Module):
+    def __init__(self, kernel, factor=2):
+        super().__init__()
+        self.factor = factor
+        self.register_buffer("kernel", make_kernel(kernel))
+        self.pad = _fir_pads(self.kernel.shape[0], factor, 1, "down")
+
+    def forward(self, input):
+        return upfirdn2d(input, self.kernel, up=1, down=self.factor, pad=self.pad)
+
+
+class Blur(nn.Module):
+    def __init__(self, kernel, pad, upsample_factor=1):
+        super().__init__()
+        kernel = make_kernel(kernel)
+        if upsample_factor > 1:
+            kernel = kernel * (upsample_factor ** 2)
+        self.register_buffer("kernel", kernel)
+        self.pad = pad
+
+    def forward(self, input):
+        return upfirdn2d(input, self.kernel, pad=self.pad)
+
+
+class EqualConv2d(nn.Module):
+    def __init__(self, in_channel, out_channel, kernel_size, stride=1, padding=0, bias=True):
+        super().__init__()
+        self.weight = nn.Parameter(torch.randn(out_channel, in_channel, kernel_size, kernel_size))
+        self.scale = 1 / math.sqrt(in_channel * kernel_size ** 2)
+        self.stride = stride
+        self.padding = padding
+        self.bias = nn.Parameter(torch.zeros(out_channel)) if bias else None
+
+    def forward(self, input):
+        return _conv.conv2d(input, self.weight * self.scale, self.bias, stride=self.stride, padding=self.padding)
+
+    def __repr__(self):
+        o, i, k, _ = self.weight.shape
+        return f"{self.__class__.__name__}({i}, {o}, {k}, stride={self.stride}, padding={self.padding})"
+
+
+class EqualLinear(nn.Module):
+    def __init__(self, in_dim, out_dim, bias=True, bias_init=0, lr_mul=1, activation=None):
+        super().__init__()
+        self.weight = nn.Parameter(torch.randn(out_dim, in_dim).div_(lr_mul))
+        self.bias = nn.Parameter(torch.zeros(out_dim).fill_(bias_init)) if bias else None
+        self.activation = activation
+        self.scale = (1 / math.sqrt(in_dim)) * lr_mul
+        self.lr_mul = lr_mul
+
+    def forward(self, input):
+        if self.activation:
+            return fused_leaky_relu(F.linear(input, self.weight * self.scale), self.bias * self.lr_mul)
+        return F.linear(input, self.weight * self.scale, bias=self.bias * self.lr_mul)
+
+    def __repr__(self):
+        return f"{self.__class__.__name__}({self.weight.shape[1]}, {self.weight.shape[0]})"
+
+
+class ScaledLeakyReLU(nn.Module):
+    def __init__(self, negative_slope=0.2):
+        super().__init__()
+        self.negative_slope = negative_slope
+
+    def forward(self, input):
+        return F.leaky_relu(input, negative_slope=self.negative_slope) * math.sqrt(2)
+
+
+class ModulatedConv2d(nn.Module):
+    def __init__(self, in_channel, out_channel, kernel_size, style_dim, demodulate=True, upsample=False,
+                 downsample=False, blur_kernel=[1, 3, 3, 1]):
+        super().__init__()
+        self.eps = 1e-8
+        self.kernel_size = kernel_size
+        self.in_channel = in_channel
+        self.out_channel = out_channel
+        self.upsample = upsample
+        self.downsample = downsample
+        if upsample:
+            self.blur = Blur(blur_kernel, pad=_fir_pads(len(blur_kernel), 2, kernel_size, "conv_up"), upsample_factor=2)
+        if downsample:
+            self.blur = Blur(blur_kernel, pad=_fir_pads(len(blur_kernel), 2, kernel_size, "conv_down"))
+        self.scale = 1 / math.sqrt(in_channel * kernel_size ** 2)
+        self.padding = kernel_size // 2
+        self.weight = nn.Parameter(torch.randn(1, out_channel, in_channel, kernel_size, kernel_size))
+        self.modulation = EqualLinear(style_dim, in_channel, bias_init=1)
+        self.demodulate = demodulate
+
+    def __repr__(self):
+        return (f"{self.__class__.__name__}({self.in_channel}, {self.out_channel}, {self.kernel_size}, "
+                f"upsample={self.upsample}, downsample={self.downsample})")
+
+    def forward(self, input, style):
+        s = self.modulation(style)                                   # (B, Cin)
+        w = self.weight[0] * self.scale                              # (Cout, Cin, k, k), shared by the batch
+        demod = None
+        if self.demodulate:
+            wsq = w.pow(2).sum([2, 3])                               # (Cout, Cin)
+            demod = torch.rsqrt(F.linear(s.pow(2), wsq) + self.eps)  # (B, Cout)
+        return _conv.modulated_conv2d(input, w, s, demod, upsample=self.upsample, downsample=self.downsample,
+                                      padding=self.padding, blur=getattr(self, "blur", None))
+
+
+class NoiseInjection(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.weight = nn.Parameter(torch.zeros(1))
+
+    def forward(self, image, noise=None):
+        if noise is None:
+            batch, _, height, width = image.shape
+            noise = image.new_empty(batch, 1, height, width).normal_()
+        return image + self.weight * noise
+
+
+class ConstantInput(nn.Module):
+    def __init__(self, channel, size=4):
+        super().__init__()
+        self.input = nn.Parameter(torch.randn(1, channel, size, size))
+
+    def forward(self, input):
+        return self.input.repeat(input.shape[0], 1, 1, 1)
+
+
+class StyledConv(nn.Module):
+    def __init__(self, in_channel, out_channel, kernel_size, style_dim, upsample=False, blur_kernel=[1, 3, 3, 1],
+                 demodulate=True):
+        super().__init__()
+        self.conv = ModulatedConv2d(in_channel, out_channel, kernel_size, style_dim, upsample=upsample,
+                                    blur_kernel=blur_kernel, demodulate=demodulate)
+        self.noise = NoiseInjection()
+        self.activate = FusedLeakyReLU(out_channel)
+
+    def forward(self, input, style, noise=None):
+        out = self.conv(input, style)
+        out = self.noise(out, noise=noise)
+        return self.activate(out)
+
+
+class ToRGB(nn.Module):
+    def __init__(self, in_channel, style_dim, upsample=True, blur_kernel=[1, 3, 3, 1]):
+        super().__init__()
+        if upsample:
+            self.upsample = Upsample(blur_kernel)
+        self.conv = ModulatedConv2d(in_channel, 3, 1, style_dim, demodulate=False)
+        self.bias = nn.Parameter(torch.zeros(1, 3, 1, 1))
+
+    def forward(self, input, style, skip=None):
+        out = self.conv(input, style) + self.bias
+        if skip is not None:
+            out = out + self.upsample(skip)
+        return out
+
+
+def _estimate_fisher(module: nn.Module, loglikelihood):
+    """Shared body of Generator/Discriminator.estimate_fisher (model_probe_tune.py:481-504, 706-729)."""
+    names = [n for n, p in module.named_parameters()]
+    grads = autograd.grad(loglikelihood, list(module.parameters()), retain_graph=True)
+    info = {n: g.detach() ** 2 for n, g, p in zip(names, grads, module.parameters()) if p.requires_grad}
+    return grads, info
+
+
+_CHANNELS = lambda cm: {4: 512, 8: 512, 16: 512, 32: 512, 64: 256 * cm, 128: 128 * cm, 256: 64 * cm,  # noqa: E731
+                        512: 32 * cm, 1024: 16 * cm}
+
+
+class Generator(nn.Module):
+    def __init__(self, size, style_dim, n_mlp, channel_multiplier=2, blur_kernel=[1, 3, 3, 1], lr_mlp=0.01):
+        super().__init__()
+        self.size = size
+        self.style_dim = style_dim
+        self.style = nn.Sequential(PixelNorm(), *[EqualLinear(style_dim, style_dim, lr_mul=lr_mlp,
+                                                              activation="fused_lrelu") for _ in range(n_mlp)])
+        self.channels = _CHANNELS(channel_multiplier)
+        self.input = ConstantInput(self.channels[4])
+        self.conv1 = StyledConv(self.channels[4], self.channels[4], 3, style_dim, blur_kernel=blur_kernel)
+        self.to_rgb1 = ToRGB(self.channels[4], style_dim, upsample=False)
+        self.log_size = int(math.log(size, 2))
+        self.num_layers = (self.log_size - 2) * 2 + 1
+        self.convs = nn.ModuleList()
+        self.upsamples = nn.ModuleList()
+        self.to_rgbs = nn.ModuleList()
+        self.noises = nn.Module()
+        for layer_idx in range(self.num_layers):
+            res = (layer_idx + 5) // 2
+            self.noises.register_buffer(f"noise_{layer_idx}", torch.randn(1, 1, 2 ** res, 2 ** res))
+        in_channel = self.channels[4]
+        for i in range(3, self.log_size + 1):
+            out_channel = self.channels[2 ** i]
+            self.convs.append(StyledConv(in_channel, out_channel, 3, style_dim, upsample=True, blur_kernel=blur_kernel))
+            self.convs.append(StyledConv(out_channel, out_channel, 3, style_dim, blur_kernel=blur_kernel))
+            self.to_rgbs.append(ToRGB(out_channel, style_dim))
+            in_channel = out_channel
+        self.n_latent = self.log_size * 2 - 2
+
+    def make_noise(self):
+        device = self.input.input.device
+        noises = [torch.randn(1, 1, 4, 4, device=device)]
+        for i in range(3, self.log_size + 1):
+            noises += [torch.randn(1, 1, 2 ** i, 2 ** i, device=device) for _ in range(2)]
+        return noises
+
+    def mean_latent(self, n_latent):
+        latent_in = torch.randn(n_latent, self.style_dim, device=self.input.input.device)
+        return self.style(latent_in).mean(0, keepdim=True)
+
+    def get_latent(self, input):
+        return self.style(input)
+
+    def estimate_fisher(self, loglikelihood):
+        return _estimate_fisher(self, loglikelihood)
+
+    def forward(self, styles, return_latents=False, inject_index=None, truncation=1, truncation_latent=None,
+                input_is_latent=False, noise=None, randomize_noise=True, return_feats=False):
+        if not input_is_latent:
+            styles = [self.style(s) for s in styles]
+        if noise is None:
+            noise = ([None] * self.num_layers if randomize_noise
+                     else [getattr(self.noises, f"noise_{i}") for i in range(self.num_layers)])
+        if truncation < 1:
+            styles = [truncation_latent + truncation * (s - truncation_latent) for s in styles]
+        if len(styles) < 2:
+            inject_index = self.n_latent
+            latent = styles[0].unsqueeze(1).repeat(1, inject_index, 1) if styles[0].ndim < 3 else styles[0]
+        else:
+            if inject_index is None:
+                inject_index = random.randint(1, self.n_latent - 1)
+            latent = torch.cat([styles[0].unsqueeze(1).repeat(1, inject_index, 1),
+                                styles[1].unsqueeze(1).repeat(1, self.n_latent - inject_index, 1)], 1)
+
+        feats: List[torch.Tensor] = []
+        out = self.input(latent)
+        out = self.conv1(out, latent[:, 0], noise=noise[0])
+        feats.append(out)
+        skip = self.to_rgb1(out, latent[:, 1])
+        i = 1
+        for up_conv, conv, n1, n2, rgb in zip(self.convs[::2], self.convs[1::2], noise[1::2], noise[2::2], self.to_rgbs):
+            out = up_conv(out, latent[:, i], noise=n1)
+            feats.append(out)
+            out = conv(out, latent[:, i + 1], noise=n2)
+            feats.append(out)
+            skip = rgb(out, latent[:, i + 2], skip)
+            i += 2
+        image = skip
+        if return_latents:
+            return image, latent
+        if return_feats:
+            return image, feats
+        return image, None
+
+
+class ConvLayer(nn.Sequential):
+    def __init__(self, in_channel, out_channel, kernel_size, downsample=False, blur_kernel=[1, 3, 3, 1], bias=True,
+                 activate=True):
+        layers = []
+        if downsample:
+            layers.append(Blur(blur_kernel, pad=_fir_pads(len(blur_kernel), 2, kernel_size, "conv_down")))
+            stride, self.padding = 2, 0
+        else:
+            stride, self.padding = 1, kernel_size // 2
+        layers.append(EqualConv2d(in_channel, out_channel, kernel_size, padding=self.padding, stride=stride,
+                                  bias=bias and not activate))
+        if activate:
+            layers.append(FusedLeakyReLU(out_channel) if bias else ScaledLeakyReLU(0.2))
+        super().__init__(*layers)
+
+
+class ResBlock(nn.Module):
+    def __init__(self, in_channel, out_channel, blur_kernel=[1, 3, 3, 1], downsample=True):
+        super().__init__()
+        self.conv1 = ConvLayer(in_channel, in_channel, 3)
+        self.conv2 = ConvLayer(in_channel, out_channel, 3, downsample=downsample)
+        self.skip = ConvLayer(in_channel, out_channel, 1, downsample=downsample, activate=False, bias=False)
+
+    def forward(self, input, feats: Optional[list] = None):
+        h1 = self.conv1(input)
+        h2 = self.conv2(h1)
+        if feats is not None:
+            feats += [h1, h2]
+        return (h2 + self.skip(input)) / math.sqrt(2)
+
+
+class Discriminator(nn.Module):
+    def __init__(self, size, channel_multiplier=2, blur_kernel=[1, 3, 3, 1]):
+        super().__init__()
+        channels = _CHANNELS(channel_multiplier)
+        convs = [ConvLayer(3, channels[size], 1)]
+        log_size = int(math.log(size, 2))
+        in_channel = channels[size]
+        for i in range(log_size, 2, -1):
+            out_channel = channels[2 ** (i - 1)]
+            convs.append(ResBlock(in_channel, out_channel, blur_kernel))
+            in_channel = out_channel
+        self.convs = nn.Sequential(*convs)
+        self.stddev_group = 25
+        self.stddev_feat = 1
+        self.final_conv = ConvLayer(in_channel + 1, channels[4], 3)
+        self.final_linear = nn.Sequential(EqualLinear(channels[4] * 4 * 4, channels[4], activation="fused_lrelu"),
+                                          EqualLinear(channels[4], 1))
+
+    def estimate_fisher(self, loglikelihood):
+        return _estimate_fisher(self, loglikelihood)
+
+    def forward(self, inp, ind=None, real=False):
+        feat: list = []
+        out = self.convs[0](inp)
+        feat.append(out)
+        for block in list(self.convs)[1:]:
+            out = block(out, feat)          # conv1 / conv2 evaluated ONCE (see module docstring)
+        batch, channel, height, width = out.shape
+        group = min(batch, self.stddev_group)
+        stddev = out.view(group, -1, self.stddev_feat, channel // self.stddev_feat, height, width)
+        stddev = torch.sqrt(stddev.var(0, unbiased=False) + 1e-8)
+        stddev = stddev.mean([2, 3, 4], keepdims=True).squeeze(2)
+        stddev = stddev.repeat(group, 1, height, width)
+        out = torch.cat([out, stddev], 1)
+        out = self.final_conv(out)
+        feat.append(out)
+        out = self.final_linear(out.view(batch, -1))
+        return out, feat

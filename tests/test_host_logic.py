@@ -1,0 +1,141 @@
+"""Host-side logic that needs no GPU: module wiring (with the two CUDA ops stubbed by the oracle -- a test of the
+Python layer, not of the kernels), draw-stream determinism, layer tables, sharding, and the world_size-2 gloo path."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from oracle import model_oracle as mo
+from oracle import ops_oracle as ops
+from oracle import synth
+
+
+@pytest.fixture()
+def cpu_stubbed(monkeypatch):
+    """Route the two custom ops to the oracle and lift the CUDA guard, so the nn.Module wiring runs on CPU."""
+    import rick_b200.conv as cv
+    import rick_b200.stylegan2 as sg
+    monkeypatch.setattr(sg, "upfirdn2d", ops.upfirdn2d)
+    monkeypatch.setattr(sg, "fused_leaky_relu", ops.fused_leaky_relu)
+    monkeypatch.setattr(sg.FusedLeakyReLU, "forward",
+                        lambda self, x: ops.fused_leaky_relu(x, self.bias, self.negative_slope, self.scale))
+    monkeypatch.setattr(cv, "_require_cuda", lambda *a: None)
+    return sg
+
+
+def test_module_wiring_matches_oracle_on_cpu(cpu_stubbed):
+    sg = cpu_stubbed
+    size = 32
+    gp, dp = synth.g_state(size, 11), synth.d_state(size, 12)
+    G, D = sg.Generator(size, 512, 8), sg.Discriminator(size)
+    G.load_state_dict(gp)
+    D.load_state_dict(dp)
+    z, z2 = synth.latents(2, 21), synth.latents(2, 22)
+    with torch.no_grad():
+        a, _ = G([z], randomize_noise=False)
+        b, _ = mo.g_forward(gp, [z], size, randomize_noise=False)
+        assert (a - b).abs().max() < 5e-5 * b.abs().max()         # algebraic modulated conv: fp32 rounding only
+        a2, lat = G([z, z2], inject_index=3, randomize_noise=False, return_latents=True)
+        b2, lat2 = mo.g_forward(gp, [z, z2], size, randomize_noise=False, inject_index=3, return_latents=True)
+        assert torch.equal(lat, lat2) and (a2 - b2).abs().max() < 5e-5 * b2.abs().max()
+        la, feat = D(b)
+        assert torch.equal(la, mo.d_forward(dp, b, size))         # D is the same arithmetic: bit-identical
+        assert len(feat) == 8
+    names = [n for n, _ in G.named_parameters()]
+    assert names == mo.g_param_names(size)
+    assert [n for n, _ in D.named_parameters()] == mo.d_param_names(size)
+
+
+def test_cuda_only_surface_raises_on_cpu():
+    from rick_b200 import op
+    with pytest.raises(RuntimeError, match="CUDA"):
+        op.upfirdn2d(torch.zeros(1, 1, 4, 4), torch.ones(4, 4))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        op.fused_leaky_relu(torch.zeros(1, 2, 4, 4), torch.zeros(2))
+    from rick_b200 import conv
+    with pytest.raises(RuntimeError, match="CUDA"):
+        conv.modulated_conv2d(torch.zeros(1, 2, 4, 4), torch.zeros(2, 2, 3, 3), torch.ones(1, 2), None)
+
+
+def test_draw_stream_is_reproducible_and_ordered():
+    from rick_b200.adapt import DrawStream
+    a, b = DrawStream(5, "cpu"), DrawStream(5, "cpu")
+    za, zb = a.mixing_latents(2, 512, 0.9), b.mixing_latents(2, 512, 0.9)
+    assert len(za) == len(zb) and all(torch.equal(x, y) for x, y in zip(za, zb))
+    assert a.randint(1, 12) == b.randint(1, 12)
+    na, nb = a.layer_noise(2, 256), b.layer_noise(2, 256)
+    assert [t.shape[-1] for t in na] == [4, 8, 8, 16, 16, 32, 32, 64, 64, 128, 128, 256, 256]
+    assert all(torch.equal(x, y) for x, y in zip(na, nb))
+    assert len(DrawStream(1, "cpu").mixing_latents(2, 8, 0.0)) == 1
+
+
+def test_layer_tables_cover_reference_keys():
+    from rick_b200 import rick
+    from oracle import rick_oracle as ro
+    g = {k: torch.from_numpy(v) for k, v in synth.fisher_g(1).items()}
+    d = {k: torch.from_numpy(v) for k, v in synth.fisher_d(2).items()}
+    gl, dl = rick.generator_layers(g), rick.discriminator_layers(d)
+    assert [l.weight for l in gl if l.group == "conv"] == ro.g_conv_keys()
+    assert [(l.weight, l.bias) for l in gl if l.group == "fc"] == ro.g_fc_keys()
+    assert [(l.weight, l.bias) for l in dl] == ro.d_layer_keys()
+    assert sum(l.rows for l in gl if l.group == "conv") == 4864
+    assert sum(l.rows for l in gl if l.group == "fc") == 5248
+    assert sum(l.rows for l in dl) == 8064
+    assert all(l.closed_low == (l.bias is None) for l in dl)
+
+
+def test_sharding_helpers():
+    from rick_b200 import dist as rd
+    n_batches = (5000 + 63) // 64
+    for world in (1, 2, 4, 8):
+        seen = sorted(sum((rd.shard_batches(n_batches, r, world) for r in range(world)), []))
+        assert seen == list(range(n_batches))
+        imgs = sorted(sum((list(rd.shard_range(5, r, world)) for r in range(world)), []))
+        assert imgs == list(range(5))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    from rick_b200 import dist as rd
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    rd.init_from_env("gloo")
+    g = torch.Generator().manual_seed(0)
+    feats = torch.randn(40, 6, generator=g, dtype=torch.float64)
+    # sample-generation statistics: each rank sees its shard of batches, one all-reduce at the end
+    st = rd.FeatureStats(6, "cpu")
+    for k in rd.shard_batches(10, rank, world):
+        st.update(feats[4 * k:4 * k + 4])
+    mu, cov = st.all_reduce().mean_cov()
+    # adaptation: gradient averaging; Fisher: accumulator sum
+    grads = [torch.full((3, 5), float(rank + 1)), torch.full((7,), float(10 * (rank + 1)))]
+    rd.allreduce_mean_(grads, bucket_bytes=32)
+    acc = [torch.full((4,), float(rank + 1))]
+    rd.allreduce_sum_(acc)
+    torch.save({"mu": mu, "cov": cov, "grads": grads, "acc": acc}, os.path.join(out_dir, f"r{rank}.pt"))
+    rd.barrier()
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_exchange_steps(tmp_path):
+    world, port = 2, _free_port()
+    mp.start_processes(_gloo_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True, start_method="spawn")
+    g = torch.Generator().manual_seed(0)
+    feats = torch.randn(40, 6, generator=g, dtype=torch.float64).numpy()
+    for r in range(world):
+        o = torch.load(os.path.join(tmp_path, f"r{r}.pt"))
+        np.testing.assert_allclose(o["mu"].numpy(), feats.mean(0), rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(o["cov"].numpy(), np.cov(feats, rowvar=False), rtol=1e-10, atol=1e-12)
+        assert torch.equal(o["grads"][0], torch.full((3, 5), 1.5)) and torch.equal(o["grads"][1], torch.full((7,), 15.0))
+        assert torch.equal(o["acc"][0], torch.full((4,), 3.0))

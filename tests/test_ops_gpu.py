@@ -1,0 +1,196 @@
+"""Parity of the sm_100a upfirdn2d / bias-act kernels (called through the C ABI) against the CPU oracle and the
+reference-generated golden vectors.  Tolerance (BASELINE.json north_star): fp32 within 1e-5 relative."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ops_oracle as ops
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+REL = 1e-5
+
+
+def _close(got, want, rel=REL):
+    want = want.to(torch.float64)
+    got = got.detach().cpu().to(torch.float64)
+    scale = max(want.abs().max().item(), 1e-30)
+    err = (got - want).abs().max().item()
+    assert err <= rel * scale, f"max-abs err {err:.3e} > {rel:.0e} * {scale:.3e}"
+
+
+@pytest.fixture(scope="module")
+def op():
+    from rick_b200 import op as _op
+    return _op
+
+
+@pytest.mark.parametrize("case", synth.UPFIRDN_CASES, ids=[c[0] for c in synth.UPFIRDN_CASES])
+def test_upfirdn2d_golden(case, golden, op):
+    name, n, c, h, w, kh, kw, up, down, p0, p1, kind = case
+    x, taps = synth.upfirdn_case_inputs(case)
+    got = op.upfirdn2d(x.cuda(), taps.cuda(), up, down, (p0, p1))
+    want = torch.from_numpy(golden("ops_golden.npz")[name])
+    assert tuple(got.shape) == tuple(want.shape)
+    _close(got, want)
+
+
+MODEL_SHAPES = [
+    # (N, C, H, W, up, down, pad, gain)  -- every call shape of G / D at 256 px, plus ragged / multi-tile ones
+    (2, 512, 9, 9, 1, 1, (1, 1), 4), (2, 512, 17, 17, 1, 1, (1, 1), 4), (2, 512, 33, 33, 1, 1, (1, 1), 4),
+    (2, 512, 65, 65, 1, 1, (1, 1), 4), (2, 256, 129, 129, 1, 1, (1, 1), 4), (2, 128, 257, 257, 1, 1, (1, 1), 4),
+    (2, 3, 4, 4, 2, 1, (2, 1), 4), (2, 3, 32, 32, 2, 1, (2, 1), 4), (2, 3, 128, 128, 2, 1, (2, 1), 4),
+    (2, 128, 256, 256, 1, 1, (2, 2), 1), (2, 128, 256, 256, 1, 1, (1, 1), 1), (2, 512, 8, 8, 1, 1, (2, 2), 1),
+    (2, 512, 8, 8, 1, 1, (1, 1), 1), (3, 7, 64, 64, 1, 2, (1, 1), 1), (1, 5, 37, 53, 2, 1, (2, 1), 4),
+    (1, 5, 37, 53, 1, 2, (2, 1), 1), (1, 4, 130, 259, 1, 1, (2, 2), 1), (1, 2, 300, 140, 2, 1, (1, 2), 4),
+    (1, 2, 31, 31, 2, 1, (-1, 3), 4), (1, 2, 40, 40, 1, 1, (-1, -2), 1),
+]
+
+
+@pytest.mark.parametrize("shape", MODEL_SHAPES, ids=[f"{s[0]}x{s[1]}x{s[2]}x{s[3]}_u{s[4]}d{s[5]}p{s[6][0]}{s[6][1]}" for s in MODEL_SHAPES])
+def test_upfirdn2d_model_shapes_fwd_bwd(shape, op):
+    n, c, h, w, up, down, pad, gain = shape
+    g = torch.Generator().manual_seed(h * 1000 + w + up * 7 + down)
+    x = torch.randn(n, c, h, w, generator=g)
+    taps = torch.tensor([1., 3., 3., 1.])
+    taps = torch.outer(taps, taps)
+    taps = taps / taps.sum() * gain
+    xo = x.clone().requires_grad_(True)
+    want = ops.upfirdn2d(xo, taps, up, down, pad)
+    xg = x.cuda().requires_grad_(True)
+    got = op.upfirdn2d(xg, taps.cuda(), up, down, pad)
+    assert tuple(got.shape) == tuple(want.shape)
+    _close(got, want.detach())
+    go = torch.randn(want.shape, generator=g)
+    (gw,) = torch.autograd.grad(want, xo, go)
+    (gg,) = torch.autograd.grad(got, xg, go.cuda())
+    _close(gg, gw)
+
+
+def test_upfirdn2d_double_backward(op):
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 3, 12, 12, generator=g)
+    taps = torch.randn(4, 4, generator=g)
+    for up, down, pad in [(2, 1, (2, 1)), (1, 2, (1, 1)), (1, 1, (2, 2))]:
+        def second_order(fn, xin, t):
+            xin = xin.clone().requires_grad_(True)
+            y = fn(xin, t, up, down, pad)
+            (gx,) = torch.autograd.grad((y ** 2).sum(), xin, create_graph=True)
+            (ggx,) = torch.autograd.grad((gx ** 3).sum(), xin)
+            return gx.detach(), ggx
+        gw, ggw = second_order(ops.upfirdn2d, x, taps)
+        gg, ggg = second_order(op.upfirdn2d, x.cuda(), taps.cuda())
+        _close(gg, gw, 1e-4)
+        _close(ggg, ggw, 1e-4)
+
+
+def test_upfirdn2d_channels_last_and_bf16(op):
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(2, 16, 20, 20, generator=g)
+    taps = torch.randn(4, 4, generator=g)
+    want = ops.upfirdn2d(x, taps, 2, 1, (2, 1))
+    got = op.upfirdn2d(x.cuda().to(memory_format=torch.channels_last), taps.cuda(), 2, 1, (2, 1))
+    assert got.is_contiguous(memory_format=torch.channels_last)
+    _close(got, want)
+    xb = x.to(torch.bfloat16)
+    wantb = ops.upfirdn2d(xb.float(), taps, 1, 1, (1, 1))
+    gotb = op.upfirdn2d(xb.cuda(), taps.cuda(), 1, 1, (1, 1))
+    assert gotb.dtype == torch.bfloat16
+    _close(gotb.float(), wantb, 1e-2)     # one bf16 rounding of the output
+
+
+def test_upfirdn2d_large_properties(op):
+    """BASELINE op-sweep size (32, 512, 128, 128) -> (32, 512, 256, 256): checked through size-independent properties
+    -- impulse response, linearity, and a strided sample against the oracle."""
+    taps = torch.tensor([1., 3., 3., 1.])
+    taps = (torch.outer(taps, taps) / 64 * 4).cuda()
+    x = torch.randn(32, 512, 128, 128, device="cuda", generator=torch.Generator("cuda").manual_seed(0))
+    y = op.upfirdn2d(x, taps, 2, 1, (2, 1))
+    assert y.shape == (32, 512, 256, 256)
+    # up=2 with gain-4 [1,3,3,1] taps preserves the plane mean up to the border
+    assert torch.allclose(y.mean(), x.mean(), atol=5e-4)
+    # linearity
+    y2 = op.upfirdn2d(x * 0.5 + 1.0, taps, 2, 1, (2, 1))
+    ones = op.upfirdn2d(torch.ones_like(x[:1, :1]), taps, 2, 1, (2, 1))
+    assert torch.allclose(y2, 0.5 * y + ones, atol=2e-5)
+    # sampled planes against the oracle
+    idx = [(0, 0), (7, 300), (31, 511)]
+    sub = torch.stack([x[a, b] for a, b in idx])[None].cpu()
+    want = ops.upfirdn2d(sub, taps.cpu(), 2, 1, (2, 1))[0]
+    got = torch.stack([y[a, b] for a, b in idx])
+    _close(got, want)
+
+
+def test_upfirdn2d_errors(op):
+    taps = torch.ones(4, 4).cuda()
+    with pytest.raises(RuntimeError):
+        op.upfirdn2d(torch.ones(1, 1, 4, 4), taps)                      # CPU input: no fallback
+    with pytest.raises(RuntimeError):
+        op.upfirdn2d(torch.ones(1, 1, 2, 2).cuda(), taps, 1, 1, (0, 0))  # empty output
+    with pytest.raises(RuntimeError):
+        op.upfirdn2d(torch.ones(1, 1, 4, 4, dtype=torch.float64).cuda(), taps)
+
+
+BIAS_SHAPES = [(2, 512), (2, 512, 4, 4), (2, 512, 32, 32), (2, 128, 256, 256), (3, 5, 7, 9), (1, 3, 1, 1), (4, 6, 2, 2),
+               (2, 4, 100, 100)]
+
+
+@pytest.mark.parametrize("shape", BIAS_SHAPES, ids=["x".join(map(str, s)) for s in BIAS_SHAPES])
+def test_fused_leaky_relu_fwd_bwd_gradgrad(shape, op):
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=g)
+    b = torch.randn(shape[1], generator=g)
+    go = torch.randn(*shape, generator=g)
+
+    def run(fn, dev):
+        xi = x.to(dev).requires_grad_(True)
+        bi = b.to(dev).requires_grad_(True)
+        gi = go.to(dev).requires_grad_(True)
+        y = fn(xi, bi)
+        gx, gb = torch.autograd.grad(y, [xi, bi], gi, create_graph=True)
+        # double backward: (gx, gb) are linear in the upstream gradient gi; differentiate w.r.t. it
+        (ggo,) = torch.autograd.grad((gx * gx).sum() + (gb * gb).sum(), gi)
+        return y.detach(), gx.detach(), gb.detach(), ggo
+
+    wy, wgx, wgb, wgg = run(ops.fused_leaky_relu, "cpu")
+    gy, ggx, ggb, ggg = run(op.fused_leaky_relu, "cuda")
+    _close(gy, wy)
+    _close(ggx, wgx)
+    _close(ggb, wgb, 1e-4)          # a sum of up to N*H*W terms in a different (fixed) order
+    _close(ggg, wgg, 1e-4)
+
+
+def test_bias_act_native_modes(op):
+    from rick_b200.op.fused_act import bias_act
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 6, 5, 8, generator=g)
+    b = torch.randn(6, generator=g)
+    ref = torch.randn(2, 6, 5, 8, generator=g)
+    for act, grad in [(3, 0), (3, 1), (3, 2), (1, 0)]:
+        want = ops.bias_act(x, b, ref, act, grad, 0.2, 2 ** 0.5)
+        got = bias_act(x.cuda(), b.cuda(), ref.cuda(), act, grad, 0.2, 2 ** 0.5)
+        _close(got, want)
+    # absent bias / ref, as the reference's empty tensors
+    _close(bias_act(x.cuda(), None, ref.cuda(), 3, 1, 0.2, 1.0), ops.bias_act(x, None, ref, 3, 1, 0.2, 1.0))
+    _close(bias_act(x.cuda(), x.new_empty(0).cuda(), None, 3, 0, 0.2, 1.0), ops.bias_act(x, None, None, 3, 0, 0.2, 1.0))
+
+
+def test_bias_act_bwd_is_deterministic(op):
+    x = torch.randn(4, 64, 64, 64, device="cuda")
+    b = torch.randn(64, device="cuda")
+    go = torch.randn_like(x)
+    outs = []
+    for _ in range(3):
+        xi, bi = x.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        gx, gb = torch.autograd.grad(op.fused_leaky_relu(xi, bi), [xi, bi], go)
+        outs.append((gx, gb))
+    assert all(torch.equal(outs[0][0], o[0]) and torch.equal(outs[0][1], o[1]) for o in outs[1:])
+
+
+def test_fused_leaky_relu_bf16(op):
+    x = torch.randn(2, 16, 8, 8).to(torch.bfloat16)
+    b = torch.randn(16).to(torch.bfloat16)
+    want = ops.fused_leaky_relu(x.float(), b.float())
+    got = op.fused_leaky_relu(x.cuda(), b.cuda())
+    assert got.dtype == torch.bfloat16
+    _close(got.float(), want, 1e-2)
