@@ -122,6 +122,65 @@ RICK_API int rick_mask_apply(float* const* param, float* const* grad, const uint
                     const uint8_t* const* zero, const int64_t* rows, const int64_t* inner, int count,
                     rick_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------- tcgen05 convolution
+ * Implicit-GEMM convolution on NHWC fp32 activations (TF32 tensor-core math, fp32 accumulate), replacing the grouped
+ * cuDNN convolutions of ModulatedConv2d (gan_training/models/model_probe_tune.py:265, 274, 280) and the dense ones
+ * of EqualConv2d (:122-128).
+ *   xm  : (batch, in_h, in_w, cin)  pre-modulated input  x[b,:,:,ci] * s[b,ci]   (or the plain input for EqualConv2d)
+ *   wt  : (n_weight_taps, cout, cin)  shared weight, one K-major matrix per filter tap
+ *   out : (batch, out_h, out_w, cout)
+ * The convolution is described as up to 4 "phases" (1 for an ordinary convolution, 4 for the polyphase form of the
+ * stride-2 transposed convolution).  Phase-local output position (m, n), m < rows, n < cols, reads input pixel
+ * (m*in_stride + dy[t], n*in_stride + dx[t]) for each tap t (out-of-range pixels count as zero) with weight matrix
+ * wt[widx[t]], and is written to output pixel (m*out_stride + out_y0, n*out_stride + out_x0).
+ * Requirements: cin % 32 == 0, cout % 128 == 0, pointers 16-byte aligned. */
+typedef struct rick_conv_phase {
+    int n_taps;
+    int dy[9], dx[9], widx[9];
+    int out_y0, out_x0;
+    int rows, cols;
+} rick_conv_phase;
+
+typedef struct rick_conv_geom {
+    int batch, in_h, in_w, cin, cout, out_h, out_w;
+    int in_stride, out_stride;
+    int n_weight_taps;
+    int n_phases;
+    rick_conv_phase phase[4];
+} rick_conv_geom;
+
+/* Fused epilogue (all pointers optional / NULL = skip):
+ *   v = acc * demod[b,co] + noise_weight[0] * noise[b,oy,ox] + bias[co];  if (act) v = (v > 0 ? v : v*alpha) * scale
+ *   out2 != NULL:  out = v;  out2 = v * s_next[b,co]   (the next layer's pre-modulated input, written in the same pass)
+ *   out2 == NULL:  out = v * s_next[b,co]              (s_next == NULL counts as 1: plain output)
+ * i.e. demodulate (model_probe_tune.py:249-251) + NoiseInjection (:293-298) + FusedLeakyReLU (op/fused_act.py). */
+typedef struct rick_conv_epilogue {
+    const float* demod;        /* (batch, cout) */
+    const float* noise;        /* (batch, out_h, out_w) */
+    const float* noise_weight; /* (1) on the device */
+    const float* bias;         /* (cout) */
+    const float* s_next;       /* (batch, cout) */
+    void* out2;                /* (batch, out_h, out_w, cout) */
+    int act;                   /* 0 = linear, 1 = leaky-ReLU */
+    float alpha, scale;
+} rick_conv_epilogue;
+
+RICK_API int rick_conv_tc(void* out, const void* xm, const void* wt, const rick_conv_geom* geom,
+                          const rick_conv_epilogue* epilogue, rick_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------- NHWC companions
+ * rick_blur_nhwc: 4x4 FIR, up = down = 1, pads (pad0, pad1) on both axes, over x (batch, in_h, in_w, channels) fp32
+ * -> out (batch, in_h+pad0+pad1-3, in_w+pad0+pad1-3, channels), with the rick_conv_epilogue fused (NULL = plain blur).
+ * Replaces Blur after the transposed conv (model_probe_tune.py:268) + NoiseInjection + FusedLeakyReLU (StyledConv,
+ * :342-348) in one pass.  channels % 4 == 0. */
+RICK_API int rick_blur_nhwc(void* out, const void* x, const float* taps, int batch, int in_h, int in_w, int channels,
+                            int pad0, int pad1, const rick_conv_epilogue* epilogue, rick_stream_t stream);
+
+/* rick_to_rgb_nhwc: ToRGB (model_probe_tune.py:361-370).  rgb[b,o,y,x] (NCHW, 3 channels) =
+ * sum_c y[b,y,x,c] * wmod[b,o,c] + bias[o] (+ skip[b,o,y,x] when skip != NULL), wmod = scale * W_rgb * style. */
+RICK_API int rick_to_rgb_nhwc(float* rgb, const float* y, const float* wmod, const float* bias, const float* skip,
+                              int batch, int h, int w, int channels, rick_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

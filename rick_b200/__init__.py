@@ -11,5 +11,6 @@ Public surface mirrors the reference (yunqing-me/RICK):
 All compute goes through the C ABI of ``librick_b200.so`` (include/rick_b200.h); there is no CPU fallback.
 """
 from . import _lib  # noqa: F401
+from . import conv_tc  # noqa: F401  (registers rick_conv_tc with the ctypes table)
 
 __version__ = "0.1.0"

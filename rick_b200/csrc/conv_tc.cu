@@ -1,0 +1,356 @@
+// Implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05 + TMEM), fed by TMA.  sm_100a only.
+//
+// Replaces the grouped cuDNN convolutions behind ModulatedConv2d (gan_training/models/model_probe_tune.py:243-284).
+// The modulation is folded into the activations (xm = x * s[b, ci]) and the demodulation into the epilogue, so the
+// batch folds into GEMM-N and no per-sample weight tensor exists:
+//
+//     D[co, pixel] = sum_{tap} sum_{ci} Wt[tap][co][ci] * xm[b, y*si + dy(tap), x*si + dx(tap), ci]
+//     out[b, oy, ox, co] = act( D * demod[b, co] + noise_w * noise[b, oy, ox] + bias[co] ) ; out2 = out * s_next[b, co]
+//
+// Layout: activations NHWC fp32 (channels innermost = GEMM-K contiguous), weights [tap][Cout][Cin] fp32; operands are
+// consumed as TF32 (kind::tf32), accumulated in fp32 in tensor memory.
+//
+// CTA = 6 warps, persistent over output tiles (grid = #SMs):
+//   warp 0  TMA producer: per (tap, 32-channel block) one weight box [128 co x 32 ci] and one activation box
+//           [nb x th x tw pixels x 32 ci], shifted by the tap offset; out-of-bounds coordinates are zero-filled by the
+//           TMA unit, which IS the convolution padding.  128-byte swizzle, 4-stage mbarrier ring.
+//   warp 1  MMA issuer: one elected thread issues 4 x tcgen05.mma (M=128, N=tile pixels, K=8) per stage into one of two
+//           TMEM accumulators; tcgen05.commit releases the smem stage / publishes the accumulator.
+//   warps 2-5  epilogue: tcgen05.ld (lane = output channel, column = pixel), fused demod / noise / bias / leaky-ReLU,
+//           coalesced NHWC stores (a warp writes 32 consecutive channels of one pixel = 128 B per instruction).
+// The transposed stride-2 convolution of the upsampling layers runs as four polyphase sub-convolutions (4/2/2/1 taps)
+// whose outputs interleave in the (2H+1)x(2W+1) result.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace rick {
+
+EncodeTiledFn get_encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kBlockM = 128;        // output channels per tile
+constexpr int kBlockK = 32;         // fp32 channels per stage = 128 B = one swizzle row
+constexpr int kMaxN = 256;          // pixels per tile
+constexpr int kABytes = kBlockM * kBlockK * 4;
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 512;      // two accumulators of up to 256 columns
+
+struct PhaseDev {
+    int n_taps;
+    int dy[9], dx[9], widx[9];
+    int out_y0, out_x0, rows, cols;
+    int tiles_y, tiles_x, tile_begin;   // tile_begin: first (pixel-)tile index of this phase
+};
+
+struct ConvDev {
+    int batch, cout, out_h, out_w, in_stride, out_stride;
+    int n_phases;
+    PhaseDev phase[4];
+    int log_tw, log_th, log_nb, n_tile;
+    int cout_tiles, kblocks, pixel_tiles, total_tiles;
+    float* out;
+    float* out2;
+    const float* demod;
+    const float* noise;
+    const float* noise_w;
+    const float* bias;
+    const float* s_next;
+    int act;
+    float alpha, scale;
+};
+
+struct TileCoord {
+    int phase, cout0, b0, y0, x0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvDev& p, int t) {
+    TileCoord c;
+    const int ct = t % p.cout_tiles;
+    int r = t / p.cout_tiles;
+    int ph = 0;
+    while (ph + 1 < p.n_phases && r >= p.phase[ph + 1].tile_begin) ++ph;
+    r -= p.phase[ph].tile_begin;
+    const PhaseDev& P = p.phase[ph];
+    const int per_img = P.tiles_y * P.tiles_x;
+    const int bt = r / per_img;
+    r -= bt * per_img;
+    c.phase = ph;
+    c.cout0 = ct * kBlockM;
+    c.b0 = bt << p.log_nb;
+    c.y0 = (r / P.tiles_x) << p.log_th;
+    c.x0 = (r % P.tiles_x) << p.log_tw;
+    return c;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
+               const __grid_constant__ ConvDev p) {
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment for the 128-byte swizzle pattern
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int b_bytes = p.n_tile * kBlockK * 4;
+    const int stage_bytes = kABytes + kMaxN * kBlockK * 4;      // fixed stride keeps every tile base 1024-aligned
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tmem_full = empty_bar + kStages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tmap_w);
+        tc::tma_prefetch_desc(&tmap_x);
+        for (int s = 0; s < kStages; ++s) {
+            tc::mbar_init(&full_bar[s], 1);
+            tc::mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(&tmem_full[s], 1);
+            tc::mbar_init(&tmem_empty[s], 4);
+        }
+        tc::fence_mbar_init();
+    }
+    if (warp == 1) {
+        tc::tmem_alloc(tmem_base_slot, kTmemCols);
+        tc::tmem_relinquish();
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const TileCoord c = decode_tile(p, t);
+                const PhaseDev& P = p.phase[c.phase];
+                for (int tap = 0; tap < P.n_taps; ++tap) {
+                    const int gx = c.x0 * p.in_stride + P.dx[tap];
+                    const int gy = c.y0 * p.in_stride + P.dy[tap];
+                    for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+                        const int s = it % kStages;
+                        tc::mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
+                        uint8_t* a_dst = smem + s * stage_bytes;
+                        uint8_t* b_dst = a_dst + kABytes;
+                        tc::mbar_arrive_expect_tx(&full_bar[s], kABytes + b_bytes);
+                        tc::tma_load_3d(a_dst, &tmap_w, &full_bar[s], kb * kBlockK, c.cout0, P.widx[tap]);
+                        tc::tma_load_4d(b_dst, &tmap_x, &full_bar[s], kb * kBlockK, gx, gy, c.b0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        const uint32_t idesc = tc::umma_idesc_tf32(kBlockM, p.n_tile);
+        uint32_t it = 0;
+        uint32_t tile_n = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_n) {
+            const TileCoord c = decode_tile(p, t);
+            const int n_kblocks = p.phase[c.phase].n_taps * p.kblocks;
+            const uint32_t acc = tile_n & 1;
+            tc::mbar_wait(&tmem_empty[acc], ((tile_n >> 1) & 1) ^ 1);
+            tc::tc_fence_after_sync();
+            const uint32_t d_tmem = tmem_base + acc * kMaxN;
+            for (int kb = 0; kb < n_kblocks; ++kb, ++it) {
+                const int s = it % kStages;
+                tc::mbar_wait(&full_bar[s], (it / kStages) & 1);
+                tc::tc_fence_after_sync();
+                if (tc::elect_one()) {
+                    const uint32_t a_addr = tc::smem_u32(smem + s * stage_bytes);
+                    const uint64_t a_desc = tc::umma_desc_k_sw128(a_addr);
+                    const uint64_t b_desc = tc::umma_desc_k_sw128(a_addr + kABytes);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 8; ++k) {
+                        // advance 8 tf32 = 32 bytes along K inside the swizzled row: +2 in the (addr >> 4) field
+                        tc::umma_tf32_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    tc::umma_commit(&empty_bar[s]);                       // smem stage reusable once these MMAs retire
+                    if (kb == n_kblocks - 1) tc::umma_commit(&tmem_full[acc]);   // accumulator complete
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===================================================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
+        const int quarter = warp & 3;
+        uint32_t tile_n = 0;
+        const int tw_mask = (1 << p.log_tw) - 1, th_mask = (1 << p.log_th) - 1;
+        const float nw = p.noise ? __ldg(p.noise_w) : 0.f;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_n) {
+            const TileCoord c = decode_tile(p, t);
+            const PhaseDev& P = p.phase[c.phase];
+            const uint32_t acc = tile_n & 1;
+            const int co = c.cout0 + quarter * 32 + lane;
+            const float bias = p.bias ? __ldg(p.bias + co) : 0.f;
+            tc::mbar_wait(&tmem_full[acc], (tile_n >> 1) & 1);
+            tc::tc_fence_after_sync();
+            const uint32_t taddr = tmem_base + acc * kMaxN + (static_cast<uint32_t>(quarter * 32) << 16);
+            int cur_b = -1;
+            float dm = 1.f, sn = 1.f;
+            for (int n0 = 0; n0 < p.n_tile; n0 += 32) {
+                uint32_t v[32];
+                tc::tmem_ld_32x32b_x32(taddr + n0, v);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int n = n0 + j;
+                    const int m_y = c.y0 + ((n >> p.log_tw) & th_mask);
+                    const int m_x = c.x0 + (n & tw_mask);
+                    const int b = c.b0 + (n >> (p.log_tw + p.log_th));
+                    if (m_y >= P.rows || m_x >= P.cols || b >= p.batch) continue;
+                    if (b != cur_b) {
+                        cur_b = b;
+                        if (p.demod) dm = __ldg(p.demod + (size_t)b * p.cout + co);
+                        if (p.s_next) sn = __ldg(p.s_next + (size_t)b * p.cout + co);
+                    }
+                    const int oy = m_y * p.out_stride + P.out_y0;
+                    const int ox = m_x * p.out_stride + P.out_x0;
+                    const size_t pix = ((size_t)b * p.out_h + oy) * p.out_w + ox;
+                    float r = __uint_as_float(v[j]) * dm;
+                    if (p.noise) r = fmaf(nw, __ldg(p.noise + pix), r);
+                    r += bias;
+                    if (p.act) r = (r > 0.f ? r : r * p.alpha) * p.scale;
+                    if (p.out2) {
+                        p.out[pix * p.cout + co] = r;
+                        p.out2[pix * p.cout + co] = r * sn;
+                    } else {
+                        p.out[pix * p.cout + co] = r * sn;     // sn == 1 unless only the modulated copy is wanted
+                    }
+                }
+            }
+            tc::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        tc::tc_fence_after_sync();
+        tc::tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+int ilog2_exact(int v) {
+    int l = 0;
+    while ((1 << l) < v) ++l;
+    return (1 << l) == v ? l : -1;
+}
+
+}  // namespace
+}  // namespace rick
+
+extern "C" int rick_conv_tc(void* out, const void* xm, const void* wt, const rick_conv_geom* g,
+                            const rick_conv_epilogue* e, rick_stream_t stream) {
+    using namespace rick;
+    if (!out || !xm || !wt || !g) return RICK_ERR_INVALID_ARGUMENT;
+    if (g->batch < 1 || g->in_h < 1 || g->in_w < 1 || g->out_h < 1 || g->out_w < 1) return RICK_ERR_INVALID_ARGUMENT;
+    if (g->n_phases < 1 || g->n_phases > 4 || g->n_weight_taps < 1) return RICK_ERR_INVALID_ARGUMENT;
+    if (g->cout % kBlockM != 0 || g->cin % kBlockK != 0) return RICK_ERR_UNSUPPORTED;
+    if (g->in_stride < 1 || g->in_stride > 2 || g->out_stride < 1 || g->out_stride > 2) return RICK_ERR_UNSUPPORTED;
+    if (!aligned_to(out, 16) || !aligned_to(xm, 16) || !aligned_to(wt, 16)) return RICK_ERR_ALIGNMENT;
+    EncodeTiledFn encode = get_encode_tiled();
+    if (!encode) return RICK_ERR_UNSUPPORTED;
+
+    // ---- pixel tile: tw x th x nb pixels (powers of two, product <= 256, multiple of 16) ----
+    int max_rows = 0, max_cols = 0;
+    for (int i = 0; i < g->n_phases; ++i) {
+        if (g->phase[i].n_taps < 1 || g->phase[i].n_taps > 9) return RICK_ERR_INVALID_ARGUMENT;
+        if (g->phase[i].rows > max_rows) max_rows = g->phase[i].rows;
+        if (g->phase[i].cols > max_cols) max_cols = g->phase[i].cols;
+    }
+    if (max_rows < 1 || max_cols < 1) return RICK_ERR_INVALID_ARGUMENT;
+    auto pow2_ceil = [](int v) { int r = 1; while (r < v) r <<= 1; return r; };
+    int tw = pow2_ceil(max_cols);
+    if (tw > 32) tw = 32;
+    if (g->in_stride == 2 && tw > 32) tw = 32;
+    int th = pow2_ceil(max_rows);
+    if (th > kMaxN / tw) th = kMaxN / tw;
+    int nb = 1;
+    while (tw * th * nb * 2 <= kMaxN && nb < pow2_ceil(g->batch)) nb <<= 1;
+    int n_tile = tw * th * nb;
+    while (n_tile < 16) { nb <<= 1; n_tile <<= 1; }     // UMMA needs N % 16 == 0 at M = 128
+    if (tw * g->in_stride > 256 || th * g->in_stride > 256) return RICK_ERR_UNSUPPORTED;
+
+    ConvDev p{};
+    p.batch = g->batch, p.cout = g->cout, p.out_h = g->out_h, p.out_w = g->out_w;
+    p.in_stride = g->in_stride, p.out_stride = g->out_stride, p.n_phases = g->n_phases;
+    p.log_tw = ilog2_exact(tw), p.log_th = ilog2_exact(th), p.log_nb = ilog2_exact(nb), p.n_tile = n_tile;
+    p.cout_tiles = g->cout / kBlockM, p.kblocks = g->cin / kBlockK;
+    int tiles = 0;
+    for (int i = 0; i < g->n_phases; ++i) {
+        PhaseDev& P = p.phase[i];
+        const rick_conv_phase& Q = g->phase[i];
+        P.n_taps = Q.n_taps;
+        for (int t = 0; t < Q.n_taps; ++t) {
+            if (Q.widx[t] < 0 || Q.widx[t] >= g->n_weight_taps) return RICK_ERR_INVALID_ARGUMENT;
+            P.dy[t] = Q.dy[t], P.dx[t] = Q.dx[t], P.widx[t] = Q.widx[t];
+        }
+        P.out_y0 = Q.out_y0, P.out_x0 = Q.out_x0, P.rows = Q.rows, P.cols = Q.cols;
+        if ((Q.rows - 1) * g->out_stride + Q.out_y0 >= g->out_h || (Q.cols - 1) * g->out_stride + Q.out_x0 >= g->out_w ||
+            Q.out_y0 < 0 || Q.out_x0 < 0)
+            return RICK_ERR_INVALID_ARGUMENT;
+        P.tiles_y = (int)ceil_div(Q.rows, th), P.tiles_x = (int)ceil_div(Q.cols, tw);
+        P.tile_begin = tiles;
+        tiles += P.tiles_y * P.tiles_x * (int)ceil_div(g->batch, nb);
+    }
+    p.pixel_tiles = tiles;
+    p.total_tiles = tiles * p.cout_tiles;
+    p.out = static_cast<float*>(out);
+    if (e) {
+        p.out2 = static_cast<float*>(e->out2), p.demod = e->demod, p.noise = e->noise, p.noise_w = e->noise_weight;
+        p.bias = e->bias, p.s_next = e->s_next, p.act = e->act, p.alpha = e->alpha, p.scale = e->scale;
+        if (p.noise && !p.noise_w) return RICK_ERR_INVALID_ARGUMENT;
+        if (p.out2 && !p.s_next) return RICK_ERR_INVALID_ARGUMENT;
+    }
+
+    // ---- tensor maps ----
+    CUtensorMap tmap_w, tmap_x;
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)g->cin, (cuuint64_t)g->cout, (cuuint64_t)g->n_weight_taps};
+        cuuint64_t strides[2] = {(cuuint64_t)g->cin * 4, (cuuint64_t)g->cin * g->cout * 4};
+        cuuint32_t box[3] = {kBlockK, kBlockM, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        if (encode(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(wt), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return RICK_ERR_INVALID_ARGUMENT;
+    }
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)g->cin, (cuuint64_t)g->in_w, (cuuint64_t)g->in_h, (cuuint64_t)g->batch};
+        cuuint64_t strides[3] = {(cuuint64_t)g->cin * 4, (cuuint64_t)g->cin * g->in_w * 4,
+                                 (cuuint64_t)g->cin * g->in_w * g->in_h * 4};
+        // with a traversal stride s the box spans tw*s input pixels and delivers ceil(box/s) = tw of them
+        cuuint32_t box[4] = {kBlockK, (cuuint32_t)(tw * g->in_stride), (cuuint32_t)(th * g->in_stride), (cuuint32_t)nb};
+        cuuint32_t estr[4] = {1, (cuuint32_t)g->in_stride, (cuuint32_t)g->in_stride, 1};
+        if (encode(&tmap_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(xm), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return RICK_ERR_INVALID_ARGUMENT;
+    }
+
+    const int stage_bytes = kABytes + kMaxN * kBlockK * 4;
+    const size_t smem = 1024 + (size_t)kStages * stage_bytes + 256;
+    RICK_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+    conv_tc_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmap_w, tmap_x, p);
+    RICK_CHECK_LAUNCH();
+    return RICK_OK;
+}

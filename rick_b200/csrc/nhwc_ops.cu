@@ -1,0 +1,201 @@
+// Channels-last (NHWC) companions of the tcgen05 convolution for the generator's fused forward path (sm_100a):
+//
+//   rick_blur_nhwc    4x4 FIR (up = down = 1, any pad) over (B, H, W, C) with the StyledConv epilogue fused in:
+//                     out = lrelu( blur(x) * demod[b,c] + noise_w * noise[b,y,x] + bias[c] ) * scale, and optionally
+//                     out2 = out * s_next[b,c] (the next layer's pre-modulated input).  This is the Blur after the
+//                     stride-2 transposed convolution (model_probe_tune.py:268) + NoiseInjection (:293-298) +
+//                     FusedLeakyReLU in ONE pass over the activation instead of four.
+//   rick_to_rgb_nhwc  ToRGB (model_probe_tune.py:361-370): 1x1 modulated conv to 3 channels (no demodulation) + bias
+//                     + the already-upsampled skip image, reading the activation exactly once.
+//
+// Both are HBM-bound streaming kernels.  Threads of a warp cover 32 consecutive float4 channel groups of one pixel,
+// so every load / store instruction moves 512 contiguous bytes.
+#include "common.cuh"
+
+namespace rick {
+namespace {
+
+struct BlurParams {
+    const float* x;
+    float* out;
+    float* out2;
+    const float* taps;   // (4,4) as registered in Blur.kernel (already includes the upsample gain)
+    const float* demod;
+    const float* noise;
+    const float* noise_w;
+    const float* bias;
+    const float* s_next;
+    int batch, in_h, in_w, out_h, out_w, c4;   // c4 = C / 4
+    int pad0;
+    int act;
+    float alpha, scale;
+    int strips_x, strips_y;                    // strips of TX output columns / TY output rows
+};
+
+constexpr int TX = 2;     // output columns per thread
+constexpr int TY = 16;    // output rows a thread marches down
+
+__device__ __forceinline__ float4 f4_fma(float4 a, float w, float4 acc) {
+    acc.x = fmaf(a.x, w, acc.x), acc.y = fmaf(a.y, w, acc.y), acc.z = fmaf(a.z, w, acc.z), acc.w = fmaf(a.w, w, acc.w);
+    return acc;
+}
+
+__global__ void __launch_bounds__(256) blur_nhwc_kernel(BlurParams p) {
+    __shared__ float s_taps[16];
+    if (threadIdx.x < 16) {   // out[y] = sum_t in[y + t - pad0] * k[3 - t]  (true convolution, as upfirdn2d)
+        const int ty = threadIdx.x >> 2, tx = threadIdx.x & 3;
+        s_taps[threadIdx.x] = __ldg(p.taps + (3 - ty) * 4 + (3 - tx));
+    }
+    __syncthreads();
+    float w[4][4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w[i >> 2][i & 3] = s_taps[i];
+
+    const long long total = (long long)p.batch * p.strips_y * p.strips_x * p.c4;
+    const float nw = p.noise ? __ldg(p.noise_w) : 0.f;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(idx % p.c4);
+        long long r = idx / p.c4;
+        const int sx = (int)(r % p.strips_x);
+        r /= p.strips_x;
+        const int sy = (int)(r % p.strips_y);
+        const int b = (int)(r / p.strips_y);
+        const int ox0 = sx * TX, oy0 = sy * TY;
+        const int ix0 = ox0 - p.pad0;
+        const float4* xin = reinterpret_cast<const float4*>(p.x) + (long long)b * p.in_h * p.in_w * p.c4 + cg;
+
+        float4 dm = make_float4(1.f, 1.f, 1.f, 1.f), bs = make_float4(0.f, 0.f, 0.f, 0.f), sn = dm;
+        if (p.demod) dm = __ldg(reinterpret_cast<const float4*>(p.demod) + (long long)b * p.c4 + cg);
+        if (p.bias) bs = __ldg(reinterpret_cast<const float4*>(p.bias) + cg);
+        if (p.s_next) sn = __ldg(reinterpret_cast<const float4*>(p.s_next) + (long long)b * p.c4 + cg);
+
+        // ring of the last 4 input rows, TX + 3 columns each
+        float4 win[4][TX + 3];
+        auto load_row = [&](int iy, float4 (&dst)[TX + 3]) {
+            const bool row_ok = iy >= 0 && iy < p.in_h;
+#pragma unroll
+            for (int c = 0; c < TX + 3; ++c) {
+                const int ix = ix0 + c;
+                dst[c] = (row_ok && ix >= 0 && ix < p.in_w) ? __ldg(xin + ((long long)iy * p.in_w + ix) * p.c4)
+                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        load_row(oy0 - p.pad0 + 0, win[0]);
+        load_row(oy0 - p.pad0 + 1, win[1]);
+        load_row(oy0 - p.pad0 + 2, win[2]);
+#pragma unroll
+        for (int dy = 0; dy < TY; ++dy) {
+            const int oy = oy0 + dy;
+            if (oy >= p.out_h) break;
+            load_row(oy - p.pad0 + 3, win[(dy + 3) & 3]);
+#pragma unroll
+            for (int ox = 0; ox < TX; ++ox) {
+                if (ox0 + ox >= p.out_w) continue;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int ty = 0; ty < 4; ++ty)
+#pragma unroll
+                    for (int tx = 0; tx < 4; ++tx) acc = f4_fma(win[(dy + ty) & 3][ox + tx], w[ty][tx], acc);
+                const long long pix = ((long long)b * p.out_h + oy) * p.out_w + (ox0 + ox);
+                const float nz = p.noise ? nw * __ldg(p.noise + pix) : 0.f;
+                float4 v;
+                v.x = fmaf(acc.x, dm.x, nz) + bs.x, v.y = fmaf(acc.y, dm.y, nz) + bs.y;
+                v.z = fmaf(acc.z, dm.z, nz) + bs.z, v.w = fmaf(acc.w, dm.w, nz) + bs.w;
+                if (p.act) {
+                    v.x = (v.x > 0.f ? v.x : v.x * p.alpha) * p.scale, v.y = (v.y > 0.f ? v.y : v.y * p.alpha) * p.scale;
+                    v.z = (v.z > 0.f ? v.z : v.z * p.alpha) * p.scale, v.w = (v.w > 0.f ? v.w : v.w * p.alpha) * p.scale;
+                }
+                const float4 vm = make_float4(v.x * sn.x, v.y * sn.y, v.z * sn.z, v.w * sn.w);
+                if (p.out2) {
+                    reinterpret_cast<float4*>(p.out)[pix * p.c4 + cg] = v;
+                    reinterpret_cast<float4*>(p.out2)[pix * p.c4 + cg] = vm;
+                } else {
+                    reinterpret_cast<float4*>(p.out)[pix * p.c4 + cg] = vm;   // sn == 1 unless only the modulated copy is wanted
+                }
+            }
+        }
+    }
+}
+
+// one warp per pixel: 3 dot products over C channels, warp-shuffle reduction
+__global__ void __launch_bounds__(256) to_rgb_nhwc_kernel(float* __restrict__ rgb, const float* __restrict__ y,
+                                                          const float* __restrict__ wmod,
+                                                          const float* __restrict__ bias,
+                                                          const float* __restrict__ skip, int batch, int hw, int c4) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long pixels = (long long)batch * hw;
+    for (long long pix = warp0; pix < pixels; pix += nwarps) {
+        const int b = (int)(pix / hw);
+        const int q = (int)(pix - (long long)b * hw);
+        const float4* a = reinterpret_cast<const float4*>(y) + pix * c4;
+        const float4* w0 = reinterpret_cast<const float4*>(wmod) + (long long)b * 3 * c4;
+        float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+        for (int i = lane; i < c4; i += 32) {
+            const float4 v = ld_stream_f4(a + i);
+            const float4 u0 = __ldg(w0 + i), u1 = __ldg(w0 + c4 + i), u2 = __ldg(w0 + 2 * c4 + i);
+            r0 += v.x * u0.x + v.y * u0.y + v.z * u0.z + v.w * u0.w;
+            r1 += v.x * u1.x + v.y * u1.y + v.z * u1.z + v.w * u1.w;
+            r2 += v.x * u2.x + v.y * u2.y + v.z * u2.z + v.w * u2.w;
+        }
+        r0 = warp_sum(r0), r1 = warp_sum(r1), r2 = warp_sum(r2);
+        if (lane < 3) {
+            float v = lane == 0 ? r0 : (lane == 1 ? r1 : r2);
+            const long long o = ((long long)b * 3 + lane) * hw + q;     // NCHW image
+            v += __ldg(bias + lane);
+            if (skip) v += __ldg(skip + o);
+            rgb[o] = v;
+        }
+    }
+}
+
+}  // namespace
+}  // namespace rick
+
+extern "C" int rick_blur_nhwc(void* out, const void* x, const float* taps, int batch, int in_h, int in_w, int channels,
+                              int pad0, int pad1, const rick_conv_epilogue* e, rick_stream_t stream) {
+    using namespace rick;
+    if (!out || !x || !taps || batch < 1 || in_h < 1 || in_w < 1 || channels < 4) return RICK_ERR_INVALID_ARGUMENT;
+    if (channels % 4 != 0) return RICK_ERR_UNSUPPORTED;
+    if (!aligned_to(out, 16) || !aligned_to(x, 16)) return RICK_ERR_ALIGNMENT;
+    BlurParams p{};
+    p.x = static_cast<const float*>(x), p.out = static_cast<float*>(out), p.taps = taps;
+    p.batch = batch, p.in_h = in_h, p.in_w = in_w, p.c4 = channels / 4, p.pad0 = pad0;
+    p.out_h = in_h + pad0 + pad1 - 4 + 1, p.out_w = in_w + pad0 + pad1 - 4 + 1;
+    if (p.out_h < 1 || p.out_w < 1) return RICK_ERR_INVALID_ARGUMENT;
+    if (e) {
+        p.out2 = static_cast<float*>(e->out2), p.demod = e->demod, p.noise = e->noise, p.noise_w = e->noise_weight;
+        p.bias = e->bias, p.s_next = e->s_next, p.act = e->act, p.alpha = e->alpha, p.scale = e->scale;
+        if (p.noise && !p.noise_w) return RICK_ERR_INVALID_ARGUMENT;
+        if (p.out2 && !p.s_next) return RICK_ERR_INVALID_ARGUMENT;
+        if ((p.demod && !aligned_to(p.demod, 16)) || (p.bias && !aligned_to(p.bias, 16)) ||
+            (p.s_next && !aligned_to(p.s_next, 16)) || (p.out2 && !aligned_to(p.out2, 16)))
+            return RICK_ERR_ALIGNMENT;
+    }
+    p.strips_x = (int)ceil_div(p.out_w, TX), p.strips_y = (int)ceil_div(p.out_h, TY);
+    const long long total = (long long)batch * p.strips_y * p.strips_x * p.c4;
+    long long blocks = ceil_div(total, 256);
+    const long long cap = (long long)kNumSMs * 32;
+    if (blocks > cap) blocks = cap;
+    blur_nhwc_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    RICK_CHECK_LAUNCH();
+    return RICK_OK;
+}
+
+extern "C" int rick_to_rgb_nhwc(float* rgb, const float* y, const float* wmod, const float* bias, const float* skip,
+                                int batch, int h, int w, int channels, rick_stream_t stream) {
+    using namespace rick;
+    if (!rgb || !y || !wmod || !bias || batch < 1 || h < 1 || w < 1 || channels < 4) return RICK_ERR_INVALID_ARGUMENT;
+    if (channels % 4 != 0) return RICK_ERR_UNSUPPORTED;
+    if (!aligned_to(y, 16) || !aligned_to(wmod, 16)) return RICK_ERR_ALIGNMENT;
+    const long long pixels = (long long)batch * h * w;
+    long long blocks = ceil_div(pixels, 8);
+    const long long cap = (long long)kNumSMs * 16;
+    if (blocks > cap) blocks = cap;
+    to_rgb_nhwc_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(rgb, y, wmod, bias, skip, batch,
+                                                                                         h * w, channels / 4);
+    RICK_CHECK_LAUNCH();
+    return RICK_OK;
+}
