@@ -181,6 +181,12 @@ RICK_API int rick_blur_nhwc(void* out, const void* x, const float* taps, int bat
 RICK_API int rick_to_rgb_nhwc(float* rgb, const float* y, const float* wmod, const float* bias, const float* skip,
                               int batch, int h, int w, int channels, rick_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------- diagnostics
+ * Hardware probe used by scripts/debug_conv_tc.py (not part of the product path): out (128,64) = a (128,32) @
+ * b[shift:shift+64] (96,32)^T through one tcgen05.mma whose B descriptor starts `shift` rows into a 128B-swizzled tile. */
+RICK_API int rick_debug_umma_shift(float* out, const float* a, const float* b, int shift, int base_offset_mode,
+                                   rick_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

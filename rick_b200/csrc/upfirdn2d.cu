@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(256) upfirdn2d_tiled(UpfirdnParams p) {
 
     // ---- stage the input tile (zero outside the image: that IS the padding) ----
     {
-        const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+        const int warp = tid >> 5, lane = tid & 31, nwarps = (blockDim.x + 31) >> 5;   // blockDim.x may be < 32
         const int rows = p.tpn * p.ith;
         const T* in = static_cast<const T*>(p.in);
         for (int row = warp; row < rows; row += nwarps) {
@@ -239,7 +239,7 @@ static int launch_tiled(UpfirdnParams p, cudaStream_t stream) {
     const int plane_floats = p.ith * p.itw_pad;
     int tpn = 256 / (txn * tyn);
     while (tpn > 1 && (size_t)tpn * plane_floats * sizeof(float) > 40 * 1024) tpn >>= 1;
-    while (tpn > 1 && (long long)(tpn >> 1) >= p.planes) tpn >>= 1;
+    while (tpn > 1 && (long long)(tpn >> 1) >= p.planes && txn * tyn * (tpn >> 1) >= 32) tpn >>= 1;
     p.tpn = tpn;
     p.tiles_x = (int)ceil_div(p.out_w, txn * OX);
     p.tiles_y = (int)ceil_div(p.out_h, tyn * OY);

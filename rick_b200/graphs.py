@@ -1,0 +1,161 @@
+"""CUDA-graph execution of the adaptation iteration.
+
+At batch 2 the iteration is launch-bound: a few thousand small kernels per step, each costing more host time than
+device time.  ``GraphedRickAdapter`` records the four sub-steps of ``RickAdapter.step`` -- D step, R1, G step,
+path-length -- once (forward, backward, mask application, fused Adam, and for the D step the weight re-pack + tcgen05
+generator forward) and replays them; EMA rides at the end of the G-step graph.  Everything data dependent is a device
+buffer written before the replay:
+
+    real images        static (B, 3, S, S) buffer, filled by ``copy_`` from the caller's tensor
+    style mixing       z1, z2 are always drawn (device RNG inside the graph); the crossover index is a device scalar,
+                       ``n_latent`` meaning "no mixing" -- latent = where(layer < index, w1, w2), which equals the
+                       reference's concat of repeats (model_probe_tune.py:544-560)
+    masks              the byte masks are device resident and updated in place by the Fisher round
+
+The Fisher round itself (once per ``fisher_freq`` iterations) stays eager.  Single-process only: with
+``world_size > 1`` use the eager ``RickAdapter`` (NCCL all-reduce between backward and the optimiser).
+"""
+from __future__ import annotations
+
+import random
+from typing import Dict
+
+import torch
+from torch import autograd, optim
+
+from . import dist as rdist
+from .adapt import (AdaptConfig, RickAdapter, d_logistic_loss, d_r1_loss, g_nonsaturating_loss, g_path_regularize)
+from .fused import FusedGenerator
+
+
+class GraphedRickAdapter(RickAdapter):
+    def __init__(self, cfg: AdaptConfig, generator, discriminator, g_ema, d_ema, fused_generator: bool = True):
+        super().__init__(cfg, generator, discriminator, g_ema, d_ema, fused_adam=True)
+        if rdist.world_size() > 1:
+            raise RuntimeError("GraphedRickAdapter is single-process; use RickAdapter under torchrun")
+        if cfg.warmup_iter != 0:
+            raise RuntimeError("GraphedRickAdapter captures the post-warm-up iteration (warmup_iter must be 0)")
+        g_ratio = cfg.g_reg_every / (cfg.g_reg_every + 1)
+        d_ratio = cfg.d_reg_every / (cfg.d_reg_every + 1)
+        self.g_optim = optim.Adam(self.g_train, lr=cfg.lr * g_ratio, betas=(0 ** g_ratio, 0.99 ** g_ratio), fused=True,
+                                  capturable=True)
+        self.d_optim = optim.Adam(self.d_train, lr=cfg.lr * d_ratio, betas=(0 ** d_ratio, 0.99 ** d_ratio), fused=True,
+                                  capturable=True)
+        dev = self.device
+        self.fg = FusedGenerator(generator) if fused_generator else None
+        self._real = torch.zeros(cfg.batch, 3, cfg.size, cfg.size, device=dev)
+        self._inject = {k: torch.full((), generator.n_latent, dtype=torch.long, device=dev) for k in ("d", "g", "path")}
+        self._layer = torch.arange(generator.n_latent, device=dev).view(1, -1, 1)
+        self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}
+        self._outs: Dict[str, Dict[str, torch.Tensor]] = {}
+        for p in list(generator.parameters()) + list(discriminator.parameters()):
+            p.requires_grad_(True)
+
+    # ---- graph bodies -----------------------------------------------------------------------------------
+    def _latent(self, batch: int, key: str) -> torch.Tensor:
+        cfg = self.cfg
+        z = torch.randn(2, batch, cfg.latent, device=self.device)
+        w1, w2 = self.g.style(z[0]), self.g.style(z[1])
+        return torch.where(self._layer < self._inject[key], w1.unsqueeze(1), w2.unsqueeze(1))
+
+    def _body_d(self):
+        cfg = self.cfg
+        with torch.no_grad():
+            latent = self._latent(cfg.batch, "d")
+            if self.fg is not None:
+                self.fg.refresh()
+                fake_img, _ = self.fg([latent], input_is_latent=True)
+            else:
+                fake_img, _ = self.g([latent], input_is_latent=True)
+        fake_pred, _ = self.d(fake_img)
+        real_pred, _ = self.d(self._real)
+        d_loss = d_logistic_loss(real_pred, fake_pred)
+        self.d.zero_grad(set_to_none=True)
+        d_loss.backward()
+        self.masks_d.apply(self.d_named, force=True)
+        self.d_optim.step()
+        return {"d": d_loss.detach(), "real_score": real_pred.mean().detach(), "fake_score": fake_pred.mean().detach()}
+
+    def _body_r1(self):
+        cfg = self.cfg
+        real_r = self._real.detach().clone().requires_grad_(True)
+        real_pred, _ = self.d(real_r)
+        real_pred = real_pred.view(real_r.size(0), -1).mean(dim=1).unsqueeze(1)
+        r1_loss = d_r1_loss(real_pred, real_r)
+        self.d.zero_grad(set_to_none=True)
+        (cfg.r1 / 2 * r1_loss * cfg.d_reg_every + 0 * real_pred[0]).backward()
+        self.masks_d.apply(self.d_named, force=True)
+        self.d_optim.step()
+        return {"r1": r1_loss.detach()}
+
+    def _body_g(self):
+        cfg = self.cfg
+        latent = self._latent(cfg.batch, "g")
+        fake_img, _ = self.g([latent], input_is_latent=True)
+        fake_pred, _ = self.d(fake_img)
+        g_loss = g_nonsaturating_loss(fake_pred)
+        self.g.zero_grad(set_to_none=True)
+        autograd.backward(g_loss, inputs=self.g_train)
+        self.masks_g.apply(self.g_named, force=True)
+        self.g_optim.step()
+        return {"g": g_loss.detach()}
+
+    def _body_path(self):
+        cfg = self.cfg
+        pb = max(1, cfg.batch // cfg.path_batch_shrink)
+        latent = self._latent(pb, "path")
+        fake_img, latents = self.g([latent], input_is_latent=True, return_latents=True)
+        path_loss, path_mean, path_lengths = g_path_regularize(fake_img, latents, self.mean_path_length,
+                                                               torch.randn_like(fake_img))
+        self.g.zero_grad(set_to_none=True)
+        weighted = cfg.path_regularize * cfg.g_reg_every * path_loss
+        if cfg.path_batch_shrink:
+            weighted = weighted + 0 * fake_img[0, 0, 0, 0]
+        autograd.backward(weighted, inputs=self.g_train)
+        self.masks_g.apply(self.g_named, force=True)
+        self.g_optim.step()
+        self.mean_path_length.copy_(path_mean)
+        return {"path": path_loss.detach(), "path_length": path_lengths.mean().detach()}
+
+    def _body_ema(self):
+        self._ema()
+        return {}
+
+    # ---- capture / replay -------------------------------------------------------------------------------
+    def _run(self, key: str):
+        if key not in self._graphs:
+            body = getattr(self, "_body_" + key)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):          # warm-up executions on a side stream (these are real training steps)
+                    body()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                outs = body()
+            self._graphs[key], self._outs[key] = graph, outs
+        self._graphs[key].replay()
+        return self._outs[key]
+
+    def _set_inject(self, key: str):
+        cfg = self.cfg
+        n = self.g.n_latent
+        v = random.randint(1, n - 1) if (cfg.mixing > 0 and random.random() < cfg.mixing) else n
+        self._inject[key].fill_(v)
+
+    def step(self, i: int, real_img: torch.Tensor, draws=None, explicit_layer_noise: bool = False):
+        cfg = self.cfg
+        self._real.copy_(real_img, non_blocking=True)
+        out: Dict[str, torch.Tensor] = {}
+        self._set_inject("d")
+        out.update(self._run("d"))
+        if i % cfg.d_reg_every == 0:
+            out.update(self._run("r1"))
+        self._set_inject("g")
+        out.update(self._run("g"))
+        if i % cfg.g_reg_every == 0:
+            self._set_inject("path")
+            out.update(self._run("path"))
+        self._run("ema")
+        return out

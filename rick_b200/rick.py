@@ -173,9 +173,11 @@ class FilterMasks:
                                            int(l.closed_low), int(self.rounds == 0), s), "rick_decide")
         self.rounds += 1
 
-    def apply(self, named_params: Dict[str, torch.nn.Parameter]):
-        """grad[freeze] = 0; param[zero] = 0; grad[zero] = 0 for every masked parameter -- one launch."""
-        if self.rounds == 0:
+    def apply(self, named_params: Dict[str, torch.nn.Parameter], force: bool = False):
+        """grad[freeze] = 0; param[zero] = 0; grad[zero] = 0 for every masked parameter -- one launch.
+        Before the first Fisher round the masks are all-zero and the call is skipped unless ``force`` (CUDA-graph
+        capture wants the launch recorded regardless)."""
+        if self.rounds == 0 and not force:
             return
         params, grads, states, zeros, rows, inner = [], [], [], [], [], []
         for name, st in self.state.items():
