@@ -208,11 +208,13 @@ def run_ours(args):
         "clocks": clocks,
     }
 
-    if rank == 0:
+    if rank == 0 and args.quick:
+        line["extra"] = {}
+    elif rank == 0:
         line["roofline"] = roofline_upfirdn2d(device)
         line["extra"] = {"op_sweep": op_sweep(device), "fisher_round_ms": time_fisher_round(adapter, fisher_lat, shots_dev),
                          "g_samples_per_s_b64_per_gpu": g_samples_per_s(Ge, device)}
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not args.quick:
             line["cpu_baseline"] = cpu_baseline(max_seconds=40.0)
     if world > 1:
         # sample generation scales by sharding batches with no communication: report the whole-job rate as well
@@ -400,6 +402,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="skip the op sweep / roofline micro-benchmarks (profiler runs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -122,23 +122,39 @@ __global__ void __launch_bounds__(256) upfirdn2d_tiled(UpfirdnParams p) {
     const int in_y0 = tile_oy0 * DOWN / UP - p.qy + WY::dmin;
 
     // ---- stage the input tile (zero outside the image: that IS the padding) ----
+    // Work items are 32-float row chunks.  Each warp issues a batch of kLoadBatch independent loads before the first
+    // shared-memory store, so ~kLoadBatch x 128 B per warp are in flight (HBM latency x bandwidth needs ~30 KB per SM).
     {
+        constexpr int kLoadBatch = 8;
         const int warp = tid >> 5, lane = tid & 31, nwarps = (blockDim.x + 31) >> 5;   // blockDim.x may be < 32
-        const int rows = p.tpn * p.ith;
+        const int cpr = (p.itw_pad + 31) >> 5;                 // chunks per staged row
+        const int nchunks = p.tpn * p.ith * cpr;
         const T* in = static_cast<const T*>(p.in);
-        for (int row = warp; row < rows; row += nwarps) {
-            const int pl = row / p.ith;
-            const int gy = in_y0 + (row - pl * p.ith);
-            const long long plane = plane0 + pl;
-            const bool row_ok = (gy >= 0) && (gy < p.in_h) && (plane < p.planes);
-            const T* src = in + (plane * p.in_h + gy) * (long long)p.in_w;
-            float* dst = smem + row * p.itw_pad;
-            for (int c = lane; c < p.itw_pad; c += 32) {
-                const int gx = in_x0 + c;
-                float v = 0.f;
-                if (row_ok && gx >= 0 && gx < p.in_w) v = Elem<T>::ld(src + gx);
-                dst[c] = v;
+        for (int c0 = warp; c0 < nchunks; c0 += nwarps * kLoadBatch) {
+            float v[kLoadBatch];
+            int dst[kLoadBatch];
+#pragma unroll
+            for (int u = 0; u < kLoadBatch; ++u) {
+                const int chunk = c0 + u * nwarps;
+                v[u] = 0.f;
+                dst[u] = -1;
+                if (chunk < nchunks) {
+                    const int row = chunk / cpr;
+                    const int col = (chunk - row * cpr) * 32 + lane;
+                    const int pl = row / p.ith;
+                    const int gy = in_y0 + (row - pl * p.ith);
+                    const int gx = in_x0 + col;
+                    const long long plane = plane0 + pl;
+                    if (col < p.itw_pad) {
+                        dst[u] = row * p.itw_pad + col;
+                        if (gy >= 0 && gy < p.in_h && gx >= 0 && gx < p.in_w && plane < p.planes)
+                            v[u] = Elem<T>::ld(in + (plane * p.in_h + gy) * (long long)p.in_w + gx);
+                    }
+                }
             }
+#pragma unroll
+            for (int u = 0; u < kLoadBatch; ++u)
+                if (dst[u] >= 0) smem[dst[u]] = v[u];
         }
     }
     __syncthreads();

@@ -139,3 +139,107 @@ def test_world_size_2_gloo_exchange_steps(tmp_path):
         np.testing.assert_allclose(o["cov"].numpy(), np.cov(feats, rowvar=False), rtol=1e-10, atol=1e-12)
         assert torch.equal(o["grads"][0], torch.full((3, 5), 1.5)) and torch.equal(o["grads"][1], torch.full((7,), 15.0))
         assert torch.equal(o["acc"][0], torch.full((4,), 3.0))
+
+
+def _emulate_conv_geom(x_nhwc, wt, g):
+    """Pure-torch reading of a rick_conv_geom (include/rick_b200.h): what rick_conv_tc must compute."""
+    b, h, w, cin = x_nhwc.shape
+    out = torch.zeros(b, g.out_h, g.out_w, g.cout, dtype=torch.float64)
+    xp = x_nhwc.double()
+    for pi in range(g.n_phases):
+        ph = g.phase[pi]
+        for m in range(ph.rows):
+            for n in range(ph.cols):
+                acc = torch.zeros(b, g.cout, dtype=torch.float64)
+                for t in range(ph.n_taps):
+                    iy, ix = m * g.in_stride + ph.dy[t], n * g.in_stride + ph.dx[t]
+                    if 0 <= iy < h and 0 <= ix < w:
+                        acc += xp[:, iy, ix, :] @ wt[ph.widx[t]].double().T
+                out[:, m * g.out_stride + ph.out_y0, n * g.out_stride + ph.out_x0, :] = acc
+    return out
+
+
+def test_conv_geometry_tables_describe_the_right_convolutions():
+    from torch.nn import functional as F
+    from rick_b200 import conv_tc as ct
+    g = torch.Generator().manual_seed(0)
+    b, cin, cout = 2, 3, 4
+    for (h, w, k, stride, pad) in [(5, 6, 3, 1, 1), (7, 7, 3, 2, 0), (6, 4, 1, 2, 0), (4, 4, 1, 1, 0)]:
+        x = torch.randn(b, cin, h, w, generator=g)
+        wgt = torch.randn(cout, cin, k, k, generator=g)
+        geom = ct.geom_conv(b, h, w, cin, cout, k, stride, pad)
+        got = _emulate_conv_geom(x.permute(0, 2, 3, 1), ct.pack_weight(wgt), geom).permute(0, 3, 1, 2)
+        want = F.conv2d(x.double(), wgt.double(), stride=stride, padding=pad)
+        assert got.shape == want.shape and torch.allclose(got, want, atol=1e-10), (h, w, k, stride, pad)
+    for (h, w) in [(4, 4), (3, 5)]:
+        x = torch.randn(b, cin, h, w, generator=g)
+        wgt = torch.randn(cout, cin, 3, 3, generator=g)
+        geom = ct.geom_conv_transpose_s2(b, h, w, cin, cout)
+        got = _emulate_conv_geom(x.permute(0, 2, 3, 1), ct.pack_weight(wgt), geom).permute(0, 3, 1, 2)
+        want = F.conv_transpose2d(x.double(), wgt.double().transpose(0, 1), stride=2, padding=0)
+        assert got.shape == want.shape == (b, cout, 2 * h + 1, 2 * w + 1) and torch.allclose(got, want, atol=1e-10)
+
+
+def _epilogue_cpu(acc, demod, noise, noise_weight, bias, act, alpha, scale, s_next, want_out2):
+    """include/rick_b200.h rick_conv_epilogue semantics on NHWC tensors."""
+    v = acc
+    if demod is not None:
+        v = v * demod[:, None, None, :]
+    if noise is not None:
+        v = v + noise_weight * noise[..., None]
+    if bias is not None:
+        v = v + bias
+    if act:
+        v = torch.where(v > 0, v, v * alpha) * scale
+    vm = v if s_next is None else v * s_next[:, None, None, :]
+    return (v, vm) if want_out2 else vm
+
+
+def test_fused_generator_plan_on_cpu(cpu_stubbed, monkeypatch):
+    """The execution plan of FusedGenerator (style indices, epilogue wiring, s_next chaining, skip upsampling) with its
+    four kernels replaced by torch emulations of their documented semantics -- host logic only, no GPU."""
+    from torch.nn import functional as F
+    import rick_b200.fused as fused
+    from rick_b200 import conv_tc as ct
+
+    def conv_stub(xm, wt, geom, demod=None, noise=None, noise_weight=None, bias=None, act=False, alpha=0.2,
+                  scale=2 ** 0.5, s_next=None, want_out2=False):
+        k = int(round(geom.n_weight_taps ** 0.5))
+        w = wt.view(k, k, geom.cout, geom.cin).permute(2, 3, 0, 1)
+        x = xm.permute(0, 3, 1, 2)
+        if geom.n_phases == 4:
+            acc = F.conv_transpose2d(x, w.transpose(0, 1), stride=2)
+        else:
+            acc = F.conv2d(x, w, stride=geom.in_stride, padding=-geom.phase[0].dy[0])
+        return _epilogue_cpu(acc.permute(0, 2, 3, 1), demod, noise, noise_weight, bias, act, alpha, scale, s_next, want_out2)
+
+    def blur_stub(x, taps, pad, demod=None, noise=None, noise_weight=None, bias=None, act=False, alpha=0.2,
+                  scale=2 ** 0.5, s_next=None, want_out2=False):
+        acc = ops.upfirdn2d(x.permute(0, 3, 1, 2), taps, pad=pad).permute(0, 2, 3, 1)
+        return _epilogue_cpu(acc, demod, noise, noise_weight, bias, act, alpha, scale, s_next, want_out2)
+
+    def rgb_stub(y, wmod, bias, skip):
+        out = torch.einsum("bhwc,boc->bohw", y, wmod) + bias[None, :, None, None]
+        return out if skip is None else out + skip
+
+    monkeypatch.setattr(ct, "conv_tc_nhwc", conv_stub)
+    monkeypatch.setattr(ct, "blur_nhwc", blur_stub)
+    monkeypatch.setattr(ct, "to_rgb_nhwc", rgb_stub)
+    monkeypatch.setattr(fused, "upfirdn2d", ops.upfirdn2d)
+    sg = cpu_stubbed
+    size = 32
+    gp = synth.g_state(size, 11)
+    G = sg.Generator(size, 512, 8)
+    G.load_state_dict(gp)
+    FG = fused.FusedGenerator(G)
+    z, z2 = synth.latents(2, 21), synth.latents(2, 22)
+    want, _ = mo.g_forward(gp, [z], size, randomize_noise=False)
+    got, none = FG([z], randomize_noise=False)
+    assert none is None and (got - want).abs().max() < 1e-4 * want.abs().max()
+    want2, lat2 = mo.g_forward(gp, [z, z2], size, randomize_noise=False, inject_index=3, return_latents=True)
+    got2, lat = FG([z, z2], randomize_noise=False, inject_index=3, return_latents=True)
+    assert torch.allclose(lat, lat2) and (got2 - want2).abs().max() < 1e-4 * want2.abs().max()
+    explicit = [torch.randn(2, 1, 2 ** r, 2 ** r) for r in [2, 3, 3, 4, 4, 5, 5]]
+    want3, _ = mo.g_forward(gp, [z], size, noise=explicit)
+    got3, _ = FG([z], noise=explicit)
+    assert (got3 - want3).abs().max() < 1e-4 * want3.abs().max()
