@@ -139,7 +139,14 @@ def run_ours(args):
     cfg = AdaptConfig(size=size, batch=batch, warmup_iter=0, fisher_freq=50, num_fisher_img=5, fisher_quantile=40.0,
                       prune_quantile=0.1, d_reg_every=16, g_reg_every=4, mixing=0.9, lr=0.002)
     G, D, Ge, De = build_networks(size, device, seed=1)       # identical weights on every rank (DDP)
-    adapter = RickAdapter(cfg, G, D, Ge, De)
+    mode = args.mode
+    if mode == "auto":
+        mode = "graphs" if world == 1 else "eager"
+    if mode == "graphs":
+        from rick_b200.graphs import GraphedRickAdapter
+        adapter = GraphedRickAdapter(cfg, G, D, Ge, De, fused_generator=True)
+    else:
+        adapter = RickAdapter(cfg, G, D, Ge, De, fused_generator=True)
     shots_host = synthetic_shots(10, size, seed=100 + rank).pin_memory()
     shots_dev = shots_host.to(device)
     fisher_lat = torch.randn(cfg.num_fisher_img, 512, generator=torch.Generator().manual_seed(7)).to(device)
@@ -178,8 +185,23 @@ def run_ours(args):
         return ms, lib.rick_launch_count() - n0
 
     W, K = args.warmup, args.steps
-    for i in range(W):
-        iteration(i, False)
+    try:
+        for i in range(W):
+            iteration(i, False)
+        if mode == "graphs":                      # make sure all four graphs exist before the timed region
+            adapter._real.copy_(shots_dev[:batch])
+            for key in ("d", "r1", "g", "path", "ema"):
+                adapter._run(key)
+    except Exception as exc:                       # graph capture refused: fall back to the eager executor, say so
+        if mode != "graphs" or args.mode == "graphs":
+            raise
+        sys.stderr.write(f"bench: CUDA-graph capture failed ({type(exc).__name__}: {exc}); falling back to eager\n")
+        torch.cuda.synchronize()
+        mode = "eager (graph capture failed)"
+        G, D, Ge, De = build_networks(size, device, seed=1)
+        adapter = RickAdapter(cfg, G, D, Ge, De, fused_generator=True)
+        for i in range(W):
+            iteration(i, False)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -198,6 +220,7 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "size": 256, "batch_per_gpu": batch, "global_batch": batch * world,
                    "parallelism": f"dp{world}", "conv_math": "tf32 (fp32 storage, fp32 accumulate)",
+                   "exec_mode": mode,
                    "timing": "inputs regenerated on device every step (fresh latents/noise); activations + weights "
                              "(~1.5 GB/iter) exceed L2",
                    "fisher_rounds_in_timed": count(W, K, cfg.fisher_freq), "r1_iters_in_timed": count(W, K, 16),
@@ -211,14 +234,18 @@ def run_ours(args):
     if rank == 0 and args.quick:
         line["extra"] = {}
     elif rank == 0:
-        line["roofline"] = roofline_upfirdn2d(device)
+        up = roofline_upfirdn2d(device)
+        tcr = roofline_conv_tc(device)
+        line["roofline"] = tcr               # dominant rick_b200 kernel of the generator forward (tensor bound)
+        line["rooflines"] = [tcr, up]        # + the memory-bound headline kernel of BASELINE.json's metric
         line["extra"] = {"op_sweep": op_sweep(device), "fisher_round_ms": time_fisher_round(adapter, fisher_lat, shots_dev),
-                         "g_samples_per_s_b64_per_gpu": g_samples_per_s(Ge, device)}
+                         "g_samples_per_s_b64_per_gpu": g_samples_per_s(Ge, device, fused=True),
+                         "g_samples_per_s_b64_per_gpu_cudnn_module_path": g_samples_per_s(Ge, device, fused=False)}
         if world == 1 and not args.no_cpu_baseline and not args.quick:
             line["cpu_baseline"] = cpu_baseline(max_seconds=40.0)
     if world > 1:
         # sample generation scales by sharding batches with no communication: report the whole-job rate as well
-        sps = g_samples_per_s(Ge, device, batches=4)
+        sps = g_samples_per_s(Ge, device, batches=4, fused=True)
         t = torch.tensor([sps], device=device)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
         if rank == 0:
@@ -314,11 +341,30 @@ def time_fisher_round(adapter, fisher_lat, shots_dev):
     return (time.perf_counter() - t) * 1e3
 
 
+def roofline_conv_tc(device):
+    """rick_conv_tc on the sample-generation shape of the 64x64 layers (batch 64, 512 -> 512, 3x3): TF32 tensor-core
+    work 2*B*H*W*Cin*Cout*9 flop per launch, CUDA events on the launching stream, L2 flushed between launches."""
+    from rick_b200 import conv_tc as ct
+    peaks = load_peaks()
+    peak = peaks["bf16_tflops"] / 2          # TF32 dense runs at half the bf16 rate; no TF32 entry in MEASURED_PEAKS.json
+    b, h, cin, cout = 64, 64, 512, 512
+    x = torch.randn(b, h, h, cin, device=device)
+    wt = torch.randn(9, cout, cin, device=device) / (cin * 9) ** 0.5
+    geom = ct.geom_conv(b, h, h, cin, cout, 3, 1, 1)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    ms = _time_kernel(lambda: ct.conv_tc_nhwc(x, wt, geom), flush)
+    flops = 2 * b * h * h * cin * cout * 9
+    achieved = flops / (ms / 1e3) / 1e12
+    return {"kernel": "conv_tc_kernel (3x3, b64 64x64 512->512)", "bound": "tensor", "achieved": achieved, "peak": peak,
+            "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": peaks["source"] + ": bf16_tflops / 2 (tf32)", "ms_per_launch": ms, "algorithmic_flops": flops}
+
+
 @torch.no_grad()
-def g_samples_per_s(G, device, batches=6, batch=64):
+def g_samples_per_s(G, device, batches=6, batch=64, fused=False):
     from rick_b200.adapt import generate_samples
     G.eval()
-    it = generate_samples(G, (batches + 2) * batch, batch, seed=1000)
+    it = generate_samples(G, (batches + 2) * batch, batch, seed=1000, fused=fused)
     next(it), next(it)
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -401,6 +447,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "graphs", "eager"],
+                    help="iteration executor: CUDA graphs (single GPU) or eager; auto = graphs when N == 1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="skip the op sweep / roofline micro-benchmarks (profiler runs)")
     args = ap.parse_args()

@@ -119,7 +119,10 @@ def g_path_regularize(fake_img, latents, mean_path_length, noise, decay=0.01):
 class RickAdapter:
     """Owns the four networks, the two Adam optimisers, the Fisher accumulators and the filter masks."""
 
-    def __init__(self, cfg: AdaptConfig, generator, discriminator, g_ema, d_ema, fused_adam: bool = True):
+    def __init__(self, cfg: AdaptConfig, generator, discriminator, g_ema, d_ema, fused_adam: bool = True,
+                 fused_generator: bool = False):
+        """``fused_generator``: produce the D step's fake batch (a no-grad generator call) with the tcgen05 executor
+        (rick_b200.fused.FusedGenerator) instead of the differentiable module path."""
         self.cfg = cfg
         self.g, self.d, self.g_ema, self.d_ema = generator, discriminator, g_ema, d_ema
         self.device = next(generator.parameters()).device
@@ -141,6 +144,10 @@ class RickAdapter:
         self.mean_path_length = torch.zeros((), device=self.device)
         self.ema_decay = 0.5 ** (32 / (10 * 1000))
         self._ema_pairs = None
+        self.fg = None
+        if fused_generator:
+            from .fused import FusedGenerator
+            self.fg = FusedGenerator(generator)
 
     # ------------------------------------------------------------------------------------------ Fisher round
     def fisher_round(self, latents: torch.Tensor, reals: torch.Tensor, layer_noise: Optional[list] = None):
@@ -200,7 +207,11 @@ class RickAdapter:
         z = draws.mixing_latents(cfg.batch, cfg.latent, cfg.mixing)
         inject = draws.randint(1, self.g.n_latent - 1) if len(z) == 2 else None
         with torch.no_grad():
-            fake_img, _ = self.g(z, inject_index=inject, noise=noise_of(cfg.batch))
+            if self.fg is not None:
+                self.fg.refresh()                       # G's weights moved since the last call
+                fake_img, _ = self.fg(z, inject_index=inject, noise=noise_of(cfg.batch))
+            else:
+                fake_img, _ = self.g(z, inject_index=inject, noise=noise_of(cfg.batch))
         fake_pred, _ = self.d(fake_img)
         real_pred, _ = self.d(real_img)
         d_loss = d_logistic_loss(real_pred, fake_pred)
@@ -285,13 +296,16 @@ class RickAdapter:
 
 @torch.no_grad()
 def generate_samples(generator, n_samples: int, batch: int, latent: int = 512, rank: int = 0, world: int = 1,
-                     seed: int = 0, to_host: bool = False):
+                     seed: int = 0, to_host: bool = False, fused: bool = False):
     """Batch-sharded sample generation (gan_training/eval.py:31-46): rank r takes batches
     r, r+W, ...; ``z`` for batch k comes from ``manual_seed(seed + k)`` so any sharding produces the same images.
     Yields (batch_index, images)."""
     device = next(generator.parameters()).device
     n_batches = (n_samples + batch - 1) // batch
     gen = torch.Generator(device=device)
+    if fused:                                   # tcgen05 executor (rick_b200.fused), same images up to TF32 rounding
+        from .fused import FusedGenerator
+        generator = FusedGenerator(generator)
     for k in range(rank, n_batches, world):
         gen.manual_seed(seed + k)
         z = torch.randn(batch, latent, generator=gen, device=device)

@@ -348,7 +348,15 @@ extern "C" int rick_conv_tc(void* out, const void* xm, const void* wt, const ric
 
     const int stage_bytes = kABytes + kMaxN * kBlockK * 4;
     const size_t smem = 1024 + (size_t)kStages * stage_bytes + 256;
-    RICK_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {   // once per device; kept out of later calls so that launches can be recorded into CUDA graphs
+        static bool attr_done[64] = {};
+        int dev = 0;
+        RICK_CUDA_TRY(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+            RICK_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (dev >= 0 && dev < 64) attr_done[dev] = true;
+        }
+    }
     int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
     conv_tc_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmap_w, tmap_x, p);
     RICK_CHECK_LAUNCH();

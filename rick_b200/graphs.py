@@ -30,7 +30,7 @@ from .fused import FusedGenerator
 
 class GraphedRickAdapter(RickAdapter):
     def __init__(self, cfg: AdaptConfig, generator, discriminator, g_ema, d_ema, fused_generator: bool = True):
-        super().__init__(cfg, generator, discriminator, g_ema, d_ema, fused_adam=True)
+        super().__init__(cfg, generator, discriminator, g_ema, d_ema, fused_adam=True, fused_generator=False)
         if rdist.world_size() > 1:
             raise RuntimeError("GraphedRickAdapter is single-process; use RickAdapter under torchrun")
         if cfg.warmup_iter != 0:

@@ -19,8 +19,8 @@ tests)
     grep -E "^(FAILED|ERROR)" $log | head -8
   done ;;
 bench)
-  timeout 600 python -u bench.py --steps ${BENCH_STEPS:-20} --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
-  echo "bench rc=$?"; tail -c 4000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err ;;
+  timeout 600 python -u bench.py --steps ${BENCH_STEPS:-20} --warmup 3 ${BENCH_ARGS} > gpurun_out/bench${BENCH_TAG}.json 2> gpurun_out/bench${BENCH_TAG}.err
+  echo "bench rc=$?"; tail -c 4500 gpurun_out/bench${BENCH_TAG}.json; tail -5 gpurun_out/bench${BENCH_TAG}.err ;;
 ncu)
   timeout 420 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches.csv \
       python -u bench.py --steps 2 --warmup 3 --no-cpu-baseline --quick > gpurun_out/ncu_bench.log 2>&1
