@@ -171,11 +171,15 @@ def run_ours(args):
         torch.cuda.synchronize()
         n0 = lib.rick_launch_count()
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if args.cuda_profiler and not e2e:
+            torch.cuda.profiler.start()           # ncu --profile-from-start off: capture exactly the timed steps
         start.record()
         for i in range(first, first + k):
             iteration(i, e2e)
         end.record()
         torch.cuda.synchronize()
+        if args.cuda_profiler and not e2e:
+            torch.cuda.profiler.stop()
         rdist.barrier()
         ms = start.elapsed_time(end)
         if world > 1:
@@ -450,6 +454,7 @@ def main():
     ap.add_argument("--mode", default="auto", choices=["auto", "graphs", "eager"],
                     help="iteration executor: CUDA graphs (single GPU) or eager; auto = graphs when N == 1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cuda-profiler", action="store_true", help="bracket the timed steps with cudaProfilerStart/Stop")
     ap.add_argument("--quick", action="store_true", help="skip the op sweep / roofline micro-benchmarks (profiler runs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
