@@ -122,39 +122,46 @@ __global__ void __launch_bounds__(256) upfirdn2d_tiled(UpfirdnParams p) {
     const int in_y0 = tile_oy0 * DOWN / UP - p.qy + WY::dmin;
 
     // ---- stage the input tile (zero outside the image: that IS the padding) ----
-    // Work items are 32-float row chunks.  Each warp issues a batch of kLoadBatch independent loads before the first
-    // shared-memory store, so ~kLoadBatch x 128 B per warp are in flight (HBM latency x bandwidth needs ~30 KB per SM).
+    // A warp owns whole tile rows (one integer divide per row, none per element) and keeps 2 rows x 4 chunks = 8
+    // independent 128-byte loads in flight before the first shared-memory store.
     {
-        constexpr int kLoadBatch = 8;
         const int warp = tid >> 5, lane = tid & 31, nwarps = (blockDim.x + 31) >> 5;   // blockDim.x may be < 32
-        const int cpr = (p.itw_pad + 31) >> 5;                 // chunks per staged row
-        const int nchunks = p.tpn * p.ith * cpr;
+        const int rows = p.tpn * p.ith;
         const T* in = static_cast<const T*>(p.in);
-        for (int c0 = warp; c0 < nchunks; c0 += nwarps * kLoadBatch) {
-            float v[kLoadBatch];
-            int dst[kLoadBatch];
+        for (int row0 = warp; row0 < rows; row0 += 2 * nwarps) {
+            long long base[2];
+            bool ok[2];
 #pragma unroll
-            for (int u = 0; u < kLoadBatch; ++u) {
-                const int chunk = c0 + u * nwarps;
-                v[u] = 0.f;
-                dst[u] = -1;
-                if (chunk < nchunks) {
-                    const int row = chunk / cpr;
-                    const int col = (chunk - row * cpr) * 32 + lane;
-                    const int pl = row / p.ith;
-                    const int gy = in_y0 + (row - pl * p.ith);
-                    const int gx = in_x0 + col;
-                    const long long plane = plane0 + pl;
-                    if (col < p.itw_pad) {
-                        dst[u] = row * p.itw_pad + col;
-                        if (gy >= 0 && gy < p.in_h && gx >= 0 && gx < p.in_w && plane < p.planes)
-                            v[u] = Elem<T>::ld(in + (plane * p.in_h + gy) * (long long)p.in_w + gx);
+            for (int r = 0; r < 2; ++r) {
+                const int row = row0 + r * nwarps;
+                const int pl = row / p.ith;
+                const int gy = in_y0 + (row - pl * p.ith);
+                const long long plane = plane0 + pl;
+                ok[r] = row < rows && gy >= 0 && gy < p.in_h && plane < p.planes;
+                base[r] = (plane * p.in_h + gy) * (long long)p.in_w + in_x0;
+            }
+            for (int c0 = lane; c0 < p.itw_pad; c0 += 128) {
+                float v[2][4];
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int c = c0 + 32 * u;
+                        const int gx = in_x0 + c;
+                        v[r][u] = (ok[r] && c < p.itw_pad && gx >= 0 && gx < p.in_w) ? Elem<T>::ld(in + base[r] + c) : 0.f;
+                    }
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const int row = row0 + r * nwarps;
+                    if (row < rows) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int c = c0 + 32 * u;
+                            if (c < p.itw_pad) smem[row * p.itw_pad + c] = v[r][u];
+                        }
                     }
                 }
             }
-#pragma unroll
-            for (int u = 0; u < kLoadBatch; ++u)
-                if (dst[u] >= 0) smem[dst[u]] = v[u];
         }
     }
     __syncthreads();

@@ -48,6 +48,8 @@ class GraphedRickAdapter(RickAdapter):
         self._layer = torch.arange(generator.n_latent, device=dev).view(1, -1, 1)
         self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}
         self._outs: Dict[str, Dict[str, torch.Tensor]] = {}
+        self._graph_launches: Dict[str, int] = {}      # rick_b200 kernel nodes recorded in each graph
+        self.replayed_launches = 0                      # rick_b200 kernels executed through graph replays so far
         for p in list(generator.parameters()) + list(discriminator.parameters()):
             p.requires_grad_(True)
 
@@ -131,11 +133,15 @@ class GraphedRickAdapter(RickAdapter):
                 for _ in range(2):          # warm-up executions on a side stream (these are real training steps)
                     body()
             torch.cuda.current_stream().wait_stream(side)
+            from . import _lib
             graph = torch.cuda.CUDAGraph()
+            n0 = _lib.lib().rick_launch_count()
             with torch.cuda.graph(graph):
                 outs = body()
+            self._graph_launches[key] = int(_lib.lib().rick_launch_count() - n0)   # launches recorded, not executed
             self._graphs[key], self._outs[key] = graph, outs
         self._graphs[key].replay()
+        self.replayed_launches += self._graph_launches[key]
         return self._outs[key]
 
     def _set_inject(self, key: str):
