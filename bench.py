@@ -243,7 +243,8 @@ def run_ours(args):
         tcr = roofline_conv_tc(device)
         line["roofline"] = tcr               # dominant rick_b200 kernel of the generator forward (tensor bound)
         line["rooflines"] = [tcr, up]        # + the memory-bound headline kernel of BASELINE.json's metric
-        line["extra"] = {"op_sweep": op_sweep(device), "fisher_round_ms": time_fisher_round(adapter, fisher_lat, shots_dev),
+        line["extra"] = {"op_sweep": op_sweep(device),
+                         "fisher_round_ms": time_fisher_round(adapter, fisher_lat, shots_dev) if world == 1 else None,
                          "g_samples_per_s_b64_per_gpu": g_samples_per_s(Ge, device, fused=True),
                          "g_samples_per_s_b64_per_gpu_cudnn_module_path": g_samples_per_s(Ge, device, fused=False)}
         if world == 1 and not args.no_cpu_baseline and not args.quick:

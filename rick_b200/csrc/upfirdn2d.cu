@@ -252,7 +252,7 @@ static int launch_tiled(UpfirdnParams p, cudaStream_t stream) {
     if (log_txn > 5) log_txn = 5;
     int log_tyn = ilog2_ceil((int)ceil_div(p.out_h, OY));
     if (log_tyn > 8 - log_txn) log_tyn = 8 - log_txn;
-    if (log_txn == 5 && log_tyn > 3) log_tyn = 3;  // 128 x 32 output tile for large maps
+    if (log_txn == 5 && log_tyn > 3) log_tyn = 3;  // 128 x (8*OY) output tile for large maps
     const int txn = 1 << log_txn, tyn = 1 << log_tyn;
     p.log_txn = log_txn;
     p.log_tyn = log_tyn;
@@ -299,10 +299,10 @@ static int dispatch(UpfirdnParams p, cudaStream_t stream) {
     const int px = floor_mod(p.pad_x0, up), py = floor_mod(p.pad_y0, up);
     if (up == 1 && p.down_x == 1) return launch_tiled<T, 1, 1, 0, 0, 4>(p, stream);
     if (up == 1 && p.down_x == 2) return launch_tiled<T, 1, 2, 0, 0, 2>(p, stream);
-    if (px == 0 && py == 0) return launch_tiled<T, 2, 1, 0, 0, 4>(p, stream);
-    if (px == 1 && py == 0) return launch_tiled<T, 2, 1, 1, 0, 4>(p, stream);
-    if (px == 0 && py == 1) return launch_tiled<T, 2, 1, 0, 1, 4>(p, stream);
-    return launch_tiled<T, 2, 1, 1, 1, 4>(p, stream);
+    if (px == 0 && py == 0) return launch_tiled<T, 2, 1, 0, 0, 8>(p, stream);
+    if (px == 1 && py == 0) return launch_tiled<T, 2, 1, 1, 0, 8>(p, stream);
+    if (px == 0 && py == 1) return launch_tiled<T, 2, 1, 0, 1, 8>(p, stream);
+    return launch_tiled<T, 2, 1, 1, 1, 8>(p, stream);
 }
 
 }  // namespace rick
