@@ -88,6 +88,13 @@ RICK_API int64_t rick_bias_act_bwd_workspace(int64_t n, int64_t c, int64_t hw);
 RICK_API int rick_bias_act_bwd(void* grad_in, float* grad_bias, void* workspace, const void* grad_out, const void* out_saved,
                       int64_t n, int64_t c, int64_t hw, float alpha, float scale, int dtype, rick_stream_t stream);
 
+/* Channels-last variant: tensors are (rows = N*H*W, C) contiguous, the bias channel is the innermost index.
+ * workspace: rick_bias_act_bwd_nhwc_workspace(rows, c) bytes.  fp32 only. */
+RICK_API int64_t rick_bias_act_bwd_nhwc_workspace(int64_t rows, int64_t c);
+RICK_API int rick_bias_act_bwd_nhwc(void* grad_in, float* grad_bias, void* workspace, const void* grad_out,
+                                    const void* out_saved, int64_t rows, int64_t c, float alpha, float scale,
+                                    rick_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------- Fisher
  * acc/grad pointer tables are HOST arrays of DEVICE pointers (count entries); they are copied into kernel
  * parameters, so no device-side table and no H2D copy is needed.
@@ -174,7 +181,8 @@ RICK_API int rick_conv_tc(void* out, const void* xm, const void* wt, const rick_
  * Replaces Blur after the transposed conv (model_probe_tune.py:268) + NoiseInjection + FusedLeakyReLU (StyledConv,
  * :342-348) in one pass.  channels % 4 == 0. */
 RICK_API int rick_blur_nhwc(void* out, const void* x, const float* taps, int batch, int in_h, int in_w, int channels,
-                            int pad0, int pad1, const rick_conv_epilogue* epilogue, rick_stream_t stream);
+                            int pad0, int pad1, int flip_taps, const rick_conv_epilogue* epilogue,
+                            rick_stream_t stream);
 
 /* rick_to_rgb_nhwc: ToRGB (model_probe_tune.py:361-370).  rgb[b,o,y,x] (NCHW, 3 channels) =
  * sum_c y[b,y,x,c] * wmod[b,o,c] + bias[o] (+ skip[b,o,y,x] when skip != NULL), wmod = scale * W_rgb * style. */

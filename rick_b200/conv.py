@@ -32,6 +32,15 @@ def _require_cuda(x: torch.Tensor, what: str):
 def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], stride: int = 1, padding: int = 0):
     """EqualConv2d's dense convolution (model_probe_tune.py:121-130)."""
     _require_cuda(x, "conv2d")
+    co, ci, kh, kw = weight.shape
+    if kh == 1 and kw == 1 and ci <= 4 and stride == 1 and padding == 0:
+        # D's from-RGB layer (3 -> C, 1x1).  As a library conv its weight gradient is a (C x 3) GEMM with
+        # K = B*H*W = 131072 that cuBLAS runs on 4 CTAs (0.96 ms per call, round-1 ncu launch list); as ci broadcast
+        # multiply-adds it is a handful of memory-bound passes and stays differentiable to any order.
+        out = x[:, 0:1] * weight[:, 0].reshape(1, co, 1, 1)
+        for c in range(1, ci):
+            out = out + x[:, c:c + 1] * weight[:, c].reshape(1, co, 1, 1)
+        return out if bias is None else out + bias.reshape(1, co, 1, 1)
     return F.conv2d(x, weight, bias=bias, stride=stride, padding=padding)
 
 

@@ -34,7 +34,7 @@ _lib._OPTIONAL["rick_conv_tc"] = (c_int, [c_void_p, c_void_p, c_void_p, ctypes.P
                                           ctypes.POINTER(ConvEpilogue), c_void_p])
 
 
-_lib._OPTIONAL["rick_blur_nhwc"] = (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+_lib._OPTIONAL["rick_blur_nhwc"] = (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                             ctypes.POINTER(ConvEpilogue), c_void_p])
 _lib._OPTIONAL["rick_to_rgb_nhwc"] = (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                               c_int, c_void_p])
@@ -122,7 +122,8 @@ def conv_tc_nhwc(xm: torch.Tensor, wt: torch.Tensor, geom: ConvGeom, demod=None,
 
 
 def blur_nhwc(x: torch.Tensor, taps: torch.Tensor, pad, demod=None, noise=None, noise_weight=None, bias=None,
-              act: bool = False, alpha: float = 0.2, scale: float = 2 ** 0.5, s_next=None, want_out2: bool = False):
+              act: bool = False, alpha: float = 0.2, scale: float = 2 ** 0.5, s_next=None, want_out2: bool = False,
+              flip: bool = False):
     """4x4 FIR over NHWC ``x`` with the StyledConv epilogue fused (see rick_blur_nhwc in include/rick_b200.h)."""
     b, h, w, c = x.shape
     oh, ow = h + pad[0] + pad[1] - 3, w + pad[0] + pad[1] - 3
@@ -132,7 +133,7 @@ def blur_nhwc(x: torch.Tensor, taps: torch.Tensor, pad, demod=None, noise=None, 
                       float(alpha), float(scale))
     with torch.cuda.device(x.device):
         st = _lib.lib().rick_blur_nhwc(out.data_ptr(), x.data_ptr(), taps.data_ptr(), b, h, w, c, pad[0], pad[1],
-                                       ctypes.byref(ep), torch.cuda.current_stream().cuda_stream)
+                                       int(flip), ctypes.byref(ep), torch.cuda.current_stream().cuda_stream)
     _lib.check(st, "rick_blur_nhwc")
     return (out, out2) if want_out2 else out
 

@@ -186,6 +186,52 @@ __global__ void __launch_bounds__(256) bias_grad_fold(float* __restrict__ grad_b
     if (lane == 0) grad_bias[ch] = acc;
 }
 
+// ---- channels-last: (rows, C) matrix, bias gradient = column sums.  A CTA owns kRowsPerCta rows; thread t owns the
+// float4 column group t % c4 and walks rows t / c4, t / c4 + lanes, ...; row-lane partials are folded through shared
+// memory and written as partial[c][cta] so that bias_grad_fold (fixed order) finishes the reduction.
+constexpr int kRowsPerCta = 128;
+
+__global__ void __launch_bounds__(256) bias_act_bwd_nhwc_main(float* __restrict__ gin, float* __restrict__ partial,
+                                                              const float* __restrict__ gout,
+                                                              const float* __restrict__ saved, long long rows, int c4,
+                                                              int nctas, float alpha, float scale) {
+    extern __shared__ float4 s_part[];            // (row_lanes, c4_tile)
+    const int c4_tile = c4 < 256 ? c4 : 256;      // column groups handled per pass
+    const int lanes = 256 / c4_tile;
+    const int cg_l = threadIdx.x % c4_tile, rl = threadIdx.x / c4_tile;
+    const long long row0 = (long long)blockIdx.x * kRowsPerCta;
+    const long long row_end = min(row0 + (long long)kRowsPerCta, rows);
+    for (int cg0 = 0; cg0 < c4; cg0 += c4_tile) {
+        const int cg = cg0 + cg_l;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rl < lanes && cg < c4) {
+            for (long long r = row0 + rl; r < row_end; r += lanes) {
+                const long long i = r * c4 + cg;
+                const float4 g = ld_stream_f4(reinterpret_cast<const float4*>(gout) + i);
+                const float4 o = ld_stream_f4(reinterpret_cast<const float4*>(saved) + i);
+                float4 v;
+                v.x = (o.x > 0.f ? g.x : g.x * alpha) * scale, v.y = (o.y > 0.f ? g.y : g.y * alpha) * scale;
+                v.z = (o.z > 0.f ? g.z : g.z * alpha) * scale, v.w = (o.w > 0.f ? g.w : g.w * alpha) * scale;
+                st_stream_f4(reinterpret_cast<float4*>(gin) + i, v);
+                acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+            }
+        }
+        if (rl < lanes) s_part[rl * c4_tile + cg_l] = acc;
+        __syncthreads();
+        if (rl == 0 && cg < c4) {
+            float4 t = s_part[cg_l];
+            for (int l = 1; l < lanes; ++l) {
+                const float4 u = s_part[l * c4_tile + cg_l];
+                t.x += u.x, t.y += u.y, t.z += u.z, t.w += u.w;
+            }
+            const long long c0 = (long long)cg * 4;
+            partial[(c0 + 0) * nctas + blockIdx.x] = t.x, partial[(c0 + 1) * nctas + blockIdx.x] = t.y;
+            partial[(c0 + 2) * nctas + blockIdx.x] = t.z, partial[(c0 + 3) * nctas + blockIdx.x] = t.w;
+        }
+        __syncthreads();
+    }
+}
+
 static inline int bwd_chunks(int64_t hw_vec) { return (int)ceil_div(hw_vec, 32 * kBwdUnroll); }
 
 template <typename T>
@@ -254,4 +300,31 @@ extern "C" int rick_bias_act_bwd(void* grad_in, float* grad_bias, void* workspac
         return launch_bias_act_bwd<float>(grad_in, grad_bias, workspace, grad_out, out_saved, n, c, hw, alpha, scale, s);
     return launch_bias_act_bwd<__nv_bfloat16>(grad_in, grad_bias, workspace, grad_out, out_saved, n, c, hw, alpha,
                                               scale, s);
+}
+
+extern "C" int64_t rick_bias_act_bwd_nhwc_workspace(int64_t rows, int64_t c) {
+    if (rows < 1 || c < 1) return 0;
+    return c * rick::ceil_div(rows, rick::kRowsPerCta) * (int64_t)sizeof(float);
+}
+
+extern "C" int rick_bias_act_bwd_nhwc(void* grad_in, float* grad_bias, void* workspace, const void* grad_out,
+                                      const void* out_saved, int64_t rows, int64_t c, float alpha, float scale,
+                                      rick_stream_t stream) {
+    using namespace rick;
+    if (!grad_in || !grad_bias || !grad_out || !out_saved || !workspace) return RICK_ERR_INVALID_ARGUMENT;
+    if (rows < 1 || c < 4 || c > 0x7fffffff) return RICK_ERR_INVALID_ARGUMENT;
+    if (c % 4 != 0) return RICK_ERR_UNSUPPORTED;
+    if (!aligned_to(grad_in, 16) || !aligned_to(grad_out, 16) || !aligned_to(out_saved, 16)) return RICK_ERR_ALIGNMENT;
+    const long long nctas = ceil_div(rows, kRowsPerCta);
+    if (nctas > 0x7fffffffLL) return RICK_ERR_OVERFLOW;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int c4 = (int)(c / 4);
+    bias_act_bwd_nhwc_main<<<(unsigned)nctas, 256, 256 * sizeof(float4), s>>>(
+        (float*)grad_in, (float*)workspace, (const float*)grad_out, (const float*)out_saved, rows, c4, (int)nctas, alpha,
+        scale);
+    RICK_CHECK_LAUNCH();
+    bias_grad_fold<float><<<(unsigned)ceil_div(c * 32, 256), 256, 0, s>>>(grad_bias, (const float*)workspace, 1, (int)c,
+                                                                          nctas);
+    RICK_CHECK_LAUNCH();
+    return RICK_OK;
 }

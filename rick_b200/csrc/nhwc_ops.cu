@@ -26,7 +26,7 @@ struct BlurParams {
     const float* bias;
     const float* s_next;
     int batch, in_h, in_w, out_h, out_w, c4;   // c4 = C / 4
-    int pad0;
+    int pad0, flip;
     int act;
     float alpha, scale;
     int strips_x, strips_y;                    // strips of TX output columns / TY output rows
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) blur_nhwc_kernel(BlurParams p) {
     __shared__ float s_taps[16];
     if (threadIdx.x < 16) {   // out[y] = sum_t in[y + t - pad0] * k[3 - t]  (true convolution, as upfirdn2d)
         const int ty = threadIdx.x >> 2, tx = threadIdx.x & 3;
-        s_taps[threadIdx.x] = __ldg(p.taps + (3 - ty) * 4 + (3 - tx));
+        s_taps[threadIdx.x] = p.flip ? __ldg(p.taps + ty * 4 + tx) : __ldg(p.taps + (3 - ty) * 4 + (3 - tx));
     }
     __syncthreads();
     float w[4][4];
@@ -155,14 +155,14 @@ __global__ void __launch_bounds__(256) to_rgb_nhwc_kernel(float* __restrict__ rg
 }  // namespace rick
 
 extern "C" int rick_blur_nhwc(void* out, const void* x, const float* taps, int batch, int in_h, int in_w, int channels,
-                              int pad0, int pad1, const rick_conv_epilogue* e, rick_stream_t stream) {
+                              int pad0, int pad1, int flip_taps, const rick_conv_epilogue* e, rick_stream_t stream) {
     using namespace rick;
     if (!out || !x || !taps || batch < 1 || in_h < 1 || in_w < 1 || channels < 4) return RICK_ERR_INVALID_ARGUMENT;
     if (channels % 4 != 0) return RICK_ERR_UNSUPPORTED;
     if (!aligned_to(out, 16) || !aligned_to(x, 16)) return RICK_ERR_ALIGNMENT;
     BlurParams p{};
     p.x = static_cast<const float*>(x), p.out = static_cast<float*>(out), p.taps = taps;
-    p.batch = batch, p.in_h = in_h, p.in_w = in_w, p.c4 = channels / 4, p.pad0 = pad0;
+    p.batch = batch, p.in_h = in_h, p.in_w = in_w, p.c4 = channels / 4, p.pad0 = pad0, p.flip = flip_taps ? 1 : 0;
     p.out_h = in_h + pad0 + pad1 - 4 + 1, p.out_w = in_w + pad0 + pad1 - 4 + 1;
     if (p.out_h < 1 || p.out_w < 1) return RICK_ERR_INVALID_ARGUMENT;
     if (e) {

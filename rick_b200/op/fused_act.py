@@ -25,11 +25,19 @@ def _check(x: torch.Tensor, what: str):
         raise RuntimeError(f"rick_b200.op.{what}: unsupported dtype {x.dtype} (float32 / bfloat16)")
 
 
+def _is_cl(x: torch.Tensor) -> bool:
+    """4-D tensor stored channels-last (and not also plain-contiguous)."""
+    return x.dim() == 4 and x.shape[1] > 1 and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last)
+
+
 def bias_act(x, bias, ref, act, grad, alpha, scale):
-    """Native-signature call: ``fused_bias_act(input, bias, refer, act, grad, alpha, scale)`` (op/fused_bias_act.cpp:11)."""
+    """Native-signature call: ``fused_bias_act(input, bias, refer, act, grad, alpha, scale)`` (op/fused_bias_act.cpp:11).
+    Channels-last inputs are processed in place of their physical (N, H, W, C) layout (bias index = innermost)."""
     _check(x, "bias_act")
-    x = x.contiguous()
-    out = torch.empty_like(x)
+    cl = _is_cl(x)
+    fmt = torch.channels_last if cl else torch.contiguous_format
+    x = x.contiguous(memory_format=fmt)
+    out = torch.empty_like(x, memory_format=fmt)
     if x.numel() == 0:
         return out
     b_ptr = r_ptr = None
@@ -41,11 +49,12 @@ def bias_act(x, bias, ref, act, grad, alpha, scale):
             raise RuntimeError(f"rick_b200.op.bias_act: bias has {size_b} entries but input dim 1 is "
                                f"{x.shape[1] if x.dim() > 1 else 'missing'}")
         step_b = 1
-        for d in x.shape[2:]:
-            step_b *= d
+        if not cl:
+            for d in x.shape[2:]:
+                step_b *= d
         b_ptr = bias.data_ptr()
     if ref is not None and ref.numel() > 0:
-        ref = ref.to(x.dtype).contiguous()
+        ref = ref.to(x.dtype).contiguous(memory_format=fmt)
         if ref.shape != x.shape:
             raise RuntimeError("rick_b200.op.bias_act: refer must have the input's shape")
         r_ptr = ref.data_ptr()
@@ -63,6 +72,23 @@ class FusedLeakyReLUFunctionBackward(Function):
         _check(grad_output, "fused_leaky_relu (backward)")
         ctx.save_for_backward(out)
         ctx.negative_slope, ctx.scale = negative_slope, scale
+        lib = _lib.lib()
+        if _is_cl(out) and out.dtype == torch.float32 and out.shape[1] % 4 == 0:
+            # channels-last: (N*H*W, C) matrix, bias gradient = column sums (rick_bias_act_bwd_nhwc)
+            g = grad_output.contiguous(memory_format=torch.channels_last)
+            c = g.shape[1]
+            rows = g.numel() // c
+            grad_input = torch.empty_like(g, memory_format=torch.channels_last)
+            grad_bias = torch.empty(c, dtype=torch.float32, device=g.device)
+            ws = torch.empty(max(int(lib.rick_bias_act_bwd_nhwc_workspace(rows, c)), 4), dtype=torch.uint8,
+                             device=g.device)
+            with torch.cuda.device(g.device):
+                st = lib.rick_bias_act_bwd_nhwc(grad_input.data_ptr(), grad_bias.data_ptr(), ws.data_ptr(), g.data_ptr(),
+                                                out.data_ptr(), rows, c, float(negative_slope), float(scale),
+                                                torch.cuda.current_stream().cuda_stream)
+            _lib.check(st, "rick_bias_act_bwd_nhwc")
+            return grad_input, grad_bias
+        out = out.contiguous()
         g = grad_output.contiguous()
         n, c = g.shape[0], g.shape[1]
         hw = 1
@@ -70,7 +96,6 @@ class FusedLeakyReLUFunctionBackward(Function):
             hw *= d
         grad_input = torch.empty_like(g)
         grad_bias = torch.empty(c, dtype=torch.float32, device=g.device)
-        lib = _lib.lib()
         ws = torch.empty(max(int(lib.rick_bias_act_bwd_workspace(n, c, hw)), 4), dtype=torch.uint8, device=g.device)
         with torch.cuda.device(g.device):
             st = lib.rick_bias_act_bwd(grad_input.data_ptr(), grad_bias.data_ptr(), ws.data_ptr(), g.data_ptr(),

@@ -42,6 +42,12 @@ def _run(x: torch.Tensor, taps: torch.Tensor, up, down, pad, flip: bool) -> torc
     if oh < 1 or ow < 1:
         raise RuntimeError(f"rick_b200.op.upfirdn2d: empty output ({oh} x {ow})")
     taps = taps.detach().to(torch.float32).contiguous()
+    if (_is_channels_last(x) and x.dtype == torch.float32 and c % 4 == 0 and (kh, kw) == (4, 4)
+            and up_x == up_y == down_x == down_y == 1 and px0 == py0 and px1 == py1):
+        # channels-last 4x4 blur: the NHWC sliding-window kernel (128-bit accesses along C)
+        from .. import conv_tc as _ct
+        out_nhwc = _ct.blur_nhwc(x.permute(0, 2, 3, 1), taps, (px0, px1), flip=flip)
+        return out_nhwc.permute(0, 3, 1, 2)           # logical NCHW view of channels-last memory
     if _is_channels_last(x):
         major, minor = n, c
         out = torch.empty((n, c, oh, ow), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)

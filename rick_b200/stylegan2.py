@@ -18,6 +18,7 @@ DESIGN.md for the per-path status).
 from __future__ import annotations
 
 import math
+import os
 import random
 from typing import List, Optional
 
@@ -27,6 +28,23 @@ from torch.nn import functional as F
 
 from . import conv as _conv
 from .op import FusedLeakyReLU, fused_leaky_relu, upfirdn2d
+
+
+# Activation memory format inside G / D.  Channels-last keeps the library convolutions in their native NHWC kernels
+# (no nchw<->nhwc transposes around every conv: ~15 % of the iteration in the round-1 launch list) and routes the
+# custom ops to their NHWC kernels.  Tensor SHAPES stay (N, C, H, W) either way.
+_CHANNELS_LAST = os.environ.get("RICK_CHANNELS_LAST", "1") != "0"
+
+
+def set_channels_last(flag: bool) -> None:
+    global _CHANNELS_LAST
+    _CHANNELS_LAST = bool(flag)
+
+
+def _fmt(x: torch.Tensor) -> torch.Tensor:
+    if _CHANNELS_LAST and x.is_cuda and x.dim() == 4:
+        return x.contiguous(memory_format=torch.channels_last)
+    return x
 
 
 def make_kernel(k):
@@ -298,7 +316,7 @@ class Generator(nn.Module):
                                 styles[1].unsqueeze(1).repeat(1, self.n_latent - inject_index, 1)], 1)
 
         feats: List[torch.Tensor] = []
-        out = self.input(latent)
+        out = _fmt(self.input(latent))
         out = self.conv1(out, latent[:, 0], noise=noise[0])
         feats.append(out)
         skip = self.to_rgb1(out, latent[:, 1])
@@ -372,7 +390,7 @@ class Discriminator(nn.Module):
 
     def forward(self, inp, ind=None, real=False):
         feat: list = []
-        out = self.convs[0](inp)
+        out = self.convs[0](_fmt(inp))
         feat.append(out)
         for block in list(self.convs)[1:]:
             out = block(out, feat)          # conv1 / conv2 evaluated ONCE (see module docstring)
@@ -385,5 +403,5 @@ class Discriminator(nn.Module):
         out = torch.cat([out, stddev], 1)
         out = self.final_conv(out)
         feat.append(out)
-        out = self.final_linear(out.view(batch, -1))
+        out = self.final_linear(out.reshape(batch, -1))      # logical (C, H, W) order whatever the memory format
         return out, feat

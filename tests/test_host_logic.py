@@ -42,7 +42,8 @@ def test_module_wiring_matches_oracle_on_cpu(cpu_stubbed):
         b2, lat2 = mo.g_forward(gp, [z, z2], size, randomize_noise=False, inject_index=3, return_latents=True)
         assert torch.equal(lat, lat2) and (a2 - b2).abs().max() < 5e-5 * b2.abs().max()
         la, feat = D(b)
-        assert torch.equal(la, mo.d_forward(dp, b, size))         # D is the same arithmetic: bit-identical
+        ld = mo.d_forward(dp, b, size)
+        assert (la - ld).abs().max() < 1e-5 * max(1.0, ld.abs().max().item())   # from-RGB layer sums in another order
         assert len(feat) == 8
     names = [n for n, _ in G.named_parameters()]
     assert names == mo.g_param_names(size)

@@ -43,7 +43,17 @@ def test_state_dict_keys_match_reference_names():
     assert sum(p.numel() for p in D.parameters()) == 28864129
 
 
-def test_generator32_and_discriminator32_vs_golden(golden):
+@pytest.mark.parametrize("channels_last", [True, False], ids=["channels_last", "nchw"])
+def test_generator32_and_discriminator32_vs_golden(golden, channels_last):
+    from rick_b200 import stylegan2 as sg
+    sg.set_channels_last(channels_last)
+    try:
+        _g32_d32(golden)
+    finally:
+        sg.set_channels_last(True)
+
+
+def _g32_d32(golden):
     gold = golden("model32_golden.npz")
     G, D, gp, dp = _build(32, 11, 12)
     z, z2, real = synth.latents(2, 21).cuda(), synth.latents(2, 22).cuda(), synth.shots(2, 32, 5).cuda()

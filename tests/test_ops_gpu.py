@@ -194,3 +194,53 @@ def test_fused_leaky_relu_bf16(op):
     got = op.fused_leaky_relu(x.cuda(), b.cuda())
     assert got.dtype == torch.bfloat16
     _close(got.float(), want, 1e-2)
+
+
+@pytest.mark.parametrize("pad", [(1, 1), (2, 2), (2, 1)])
+def test_upfirdn2d_channels_last_blur_fwd_bwd_gradgrad(pad, op):
+    """channels-last 4x4 blur goes through rick_blur_nhwc; all derivative orders against the oracle."""
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 16, 13, 9, generator=g)
+    taps = torch.randn(4, 4, generator=g)            # asymmetric taps: catches a wrong flip in the adjoint
+
+    def run(fn, xin, t):
+        xin = xin.requires_grad_(True)
+        y = fn(xin, t, 1, 1, pad)
+        (gx,) = torch.autograd.grad((y ** 2).sum(), xin, create_graph=True)
+        (ggx,) = torch.autograd.grad((gx ** 3).sum(), xin)
+        return y.detach(), gx.detach(), ggx
+
+    wy, wg, wgg = run(ops.upfirdn2d, x.clone(), taps)
+    xc = x.cuda().to(memory_format=torch.channels_last)
+    gy, gg, ggg = run(op.upfirdn2d, xc, taps.cuda())
+    assert gy.is_contiguous(memory_format=torch.channels_last)
+    _close(gy, wy)
+    _close(gg, wg, 1e-4)
+    _close(ggg, wgg, 1e-4)
+
+
+@pytest.mark.parametrize("shape", [(2, 512, 4, 4), (2, 128, 64, 64), (3, 12, 7, 9), (2, 256, 33, 33)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_fused_leaky_relu_channels_last(shape, op):
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=g)
+    b = torch.randn(shape[1], generator=g)
+    go = torch.randn(*shape, generator=g)
+
+    def run(fn, dev, cl):
+        conv = (lambda t: t.to(dev).to(memory_format=torch.channels_last)) if cl else (lambda t: t.to(dev))
+        xi = conv(x).requires_grad_(True)
+        bi = b.to(dev).requires_grad_(True)
+        gi = conv(go).requires_grad_(True)
+        y = fn(xi, bi)
+        gx, gb = torch.autograd.grad(y, [xi, bi], gi, create_graph=True)
+        (ggo,) = torch.autograd.grad((gx * gx).sum() + (gb * gb).sum(), gi)
+        return y, gx.detach(), gb.detach(), ggo
+
+    wy, wgx, wgb, wgg = run(ops.fused_leaky_relu, "cpu", False)
+    gy, ggx, ggb, ggg = run(op.fused_leaky_relu, "cuda", True)
+    assert gy.is_contiguous(memory_format=torch.channels_last) and ggx.is_contiguous(memory_format=torch.channels_last)
+    _close(gy, wy.detach())
+    _close(ggx, wgx)
+    _close(ggb, wgb, 1e-4)
+    _close(ggg, wgg, 1e-4)
