@@ -324,6 +324,22 @@ def op_sweep(device):
     out["d_blur_pad22_128->129"] = 4 * n * c * (128 * 128 + 129 * 129) / ms / 1e6
     ms = _time_kernel(lambda: op.upfirdn2d(x, taps1, down=2, pad=(1, 1)), flush, iters=5)
     out["down2_128->64"] = 4 * n * c * (128 * 128 + 64 * 64) / ms / 1e6
+    from rick_b200 import conv_tc as ct
+    xn = torch.randn(n, 129, 129, c, device=device)                       # NHWC blur after the transposed conv
+    ms = _time_kernel(lambda: ct.blur_nhwc(xn, taps4, (1, 1)), flush, iters=5)
+    out["blur_nhwc_129->128"] = 4 * n * c * (129 * 129 + 128 * 128) / ms / 1e6
+    del xn
+    xcl = torch.randn(n, c, 128, 128, device=device).to(memory_format=torch.channels_last)
+    bcl = torch.randn(c, device=device)
+    ms = _time_kernel(lambda: op.fused_leaky_relu(xcl, bcl), flush, iters=5)
+    out["bias_act_fwd_nhwc_128"] = 4 * 2 * xcl.numel() / ms / 1e6
+    xr = xcl.clone().requires_grad_(True)
+    br = bcl.clone().requires_grad_(True)
+    y = op.fused_leaky_relu(xr, br)
+    go = torch.randn_like(y)
+    ms = _time_kernel(lambda: torch.autograd.grad(y, [xr, br], go, retain_graph=True), flush, iters=5)
+    out["bias_act_bwd_nhwc_128"] = 4 * 3 * xcl.numel() / ms / 1e6
+    del xcl, xr, y, go
     b = torch.randn(c, device=device)
     for r in (16, 128):
         xa = torch.randn(n, c, r, r, device=device)

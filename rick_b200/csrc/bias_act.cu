@@ -75,6 +75,26 @@ __global__ void __launch_bounds__(256) bias_act_vec(T* __restrict__ out, const T
     }
 }
 
+// channels-last fp32: step_b == 1, the 4 lanes of a vector are 4 consecutive channels -> bias is a float4 at i % c4
+__global__ void __launch_bounds__(256) bias_act_vec_nhwc(float* __restrict__ out, const float* __restrict__ x,
+                                                         const float* __restrict__ bias, const float* __restrict__ ref,
+                                                         long long nvec, int c4, int act, int grad, float alpha,
+                                                         float scale) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        float4 v = ld_stream_f4(reinterpret_cast<const float4*>(x) + i);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + (int)(i % c4));
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ref) r = ld_stream_f4(reinterpret_cast<const float4*>(ref) + i);
+        v.x += b.x, v.y += b.y, v.z += b.z, v.w += b.w;
+        v.x = act_apply(v.x, grad == 0 ? v.x : r.x, act, grad, alpha) * scale;
+        v.y = act_apply(v.y, grad == 0 ? v.y : r.y, act, grad, alpha) * scale;
+        v.z = act_apply(v.z, grad == 0 ? v.z : r.z, act, grad, alpha) * scale;
+        v.w = act_apply(v.w, grad == 0 ? v.w : r.w, act, grad, alpha) * scale;
+        st_stream_f4(reinterpret_cast<float4*>(out) + i, v);
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) bias_act_scalar(T* __restrict__ out, const T* __restrict__ x,
                                                        const T* __restrict__ bias, const T* __restrict__ ref,
@@ -96,6 +116,17 @@ static int launch_bias_act(void* out, const void* x, const void* bias, const voi
     const bool vec = (n % N == 0) && (!bias || step_b % N == 0) && aligned_to(out, 16) && aligned_to(x, 16) &&
                      (!ref || aligned_to(ref, 16));
     const long long cap = (long long)kNumSMs * 16;
+    if (sizeof(T) == 4 && bias && step_b == 1 && size_b % 4 == 0 && n % 4 == 0 && aligned_to(out, 16) &&
+        aligned_to(x, 16) && aligned_to(bias, 16) && (!ref || aligned_to(ref, 16))) {
+        const long long nvec = n / 4;
+        long long blocks = ceil_div(nvec, 256);
+        if (blocks > cap) blocks = cap;
+        bias_act_vec_nhwc<<<(unsigned)blocks, 256, 0, s>>>((float*)out, (const float*)x, (const float*)bias,
+                                                            (const float*)ref, nvec, (int)(size_b / 4), act, grad, alpha,
+                                                            scale);
+        RICK_CHECK_LAUNCH();
+        return RICK_OK;
+    }
     if (vec) {
         const long long nvec = n / N;
         long long blocks = ceil_div(nvec, 256);

@@ -40,7 +40,10 @@ __device__ __forceinline__ float4 f4_fma(float4 a, float w, float4 acc) {
     return acc;
 }
 
-__global__ void __launch_bounds__(256) blur_nhwc_kernel(BlurParams p) {
+// Thread = one float4 channel group x TX output columns, marching down TY output rows with a ring of 5 input rows in
+// registers: while output row dy is computed from rows dy..dy+3, the loads of row dy+4 are already in flight
+// (software prefetch), so each warp keeps >= (TX+3) x 512 B outstanding.  128-thread CTAs, 3 per SM.
+__global__ void __launch_bounds__(128, 3) blur_nhwc_kernel(BlurParams p) {
     __shared__ float s_taps[16];
     if (threadIdx.x < 16) {   // out[y] = sum_t in[y + t - pad0] * k[3 - t]  (true convolution, as upfirdn2d)
         const int ty = threadIdx.x >> 2, tx = threadIdx.x & 3;
@@ -62,7 +65,7 @@ __global__ void __launch_bounds__(256) blur_nhwc_kernel(BlurParams p) {
         const int sy = (int)(r % p.strips_y);
         const int b = (int)(r / p.strips_y);
         const int ox0 = sx * TX, oy0 = sy * TY;
-        const int ix0 = ox0 - p.pad0;
+        const int ix0 = ox0 - p.pad0, iy0 = oy0 - p.pad0;
         const float4* xin = reinterpret_cast<const float4*>(p.x) + (long long)b * p.in_h * p.in_w * p.c4 + cg;
 
         float4 dm = make_float4(1.f, 1.f, 1.f, 1.f), bs = make_float4(0.f, 0.f, 0.f, 0.f), sn = dm;
@@ -70,25 +73,29 @@ __global__ void __launch_bounds__(256) blur_nhwc_kernel(BlurParams p) {
         if (p.bias) bs = __ldg(reinterpret_cast<const float4*>(p.bias) + cg);
         if (p.s_next) sn = __ldg(reinterpret_cast<const float4*>(p.s_next) + (long long)b * p.c4 + cg);
 
-        // ring of the last 4 input rows, TX + 3 columns each
-        float4 win[4][TX + 3];
-        auto load_row = [&](int iy, float4 (&dst)[TX + 3]) {
-            const bool row_ok = iy >= 0 && iy < p.in_h;
+        bool col_ok[TX + 3];
 #pragma unroll
-            for (int c = 0; c < TX + 3; ++c) {
-                const int ix = ix0 + c;
-                dst[c] = (row_ok && ix >= 0 && ix < p.in_w) ? __ldg(xin + ((long long)iy * p.in_w + ix) * p.c4)
-                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+        for (int c = 0; c < TX + 3; ++c) col_ok[c] = (ix0 + c >= 0) && (ix0 + c < p.in_w);
+        const int rows_here = min(TY, p.out_h - oy0);          // output rows this thread produces
+
+        float4 ring[5][TX + 3];
+        auto load_row = [&](int rel, float4 (&dst)[TX + 3]) {  // input row iy0 + rel
+            const int iy = iy0 + rel;
+            const bool row_ok = iy >= 0 && iy < p.in_h && rel < rows_here + 3;
+            const float4* rowp = xin + ((long long)iy * p.in_w + ix0) * p.c4;
+#pragma unroll
+            for (int c = 0; c < TX + 3; ++c)
+                dst[c] = (row_ok && col_ok[c]) ? __ldg(rowp + (long long)c * p.c4) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
-        load_row(oy0 - p.pad0 + 0, win[0]);
-        load_row(oy0 - p.pad0 + 1, win[1]);
-        load_row(oy0 - p.pad0 + 2, win[2]);
+        load_row(0, ring[0]);
+        load_row(1, ring[1]);
+        load_row(2, ring[2]);
+        load_row(3, ring[3]);
 #pragma unroll
         for (int dy = 0; dy < TY; ++dy) {
+            if (dy >= rows_here) break;
+            load_row(dy + 4, ring[(dy + 4) % 5]);              // prefetch: consumed by the NEXT iteration
             const int oy = oy0 + dy;
-            if (oy >= p.out_h) break;
-            load_row(oy - p.pad0 + 3, win[(dy + 3) & 3]);
 #pragma unroll
             for (int ox = 0; ox < TX; ++ox) {
                 if (ox0 + ox >= p.out_w) continue;
@@ -96,7 +103,7 @@ __global__ void __launch_bounds__(256) blur_nhwc_kernel(BlurParams p) {
 #pragma unroll
                 for (int ty = 0; ty < 4; ++ty)
 #pragma unroll
-                    for (int tx = 0; tx < 4; ++tx) acc = f4_fma(win[(dy + ty) & 3][ox + tx], w[ty][tx], acc);
+                    for (int tx = 0; tx < 4; ++tx) acc = f4_fma(ring[(dy + ty) % 5][ox + tx], w[ty][tx], acc);
                 const long long pix = ((long long)b * p.out_h + oy) * p.out_w + (ox0 + ox);
                 const float nz = p.noise ? nw * __ldg(p.noise + pix) : 0.f;
                 float4 v;
@@ -108,10 +115,10 @@ __global__ void __launch_bounds__(256) blur_nhwc_kernel(BlurParams p) {
                 }
                 const float4 vm = make_float4(v.x * sn.x, v.y * sn.y, v.z * sn.z, v.w * sn.w);
                 if (p.out2) {
-                    reinterpret_cast<float4*>(p.out)[pix * p.c4 + cg] = v;
-                    reinterpret_cast<float4*>(p.out2)[pix * p.c4 + cg] = vm;
+                    st_stream_f4(reinterpret_cast<float4*>(p.out) + pix * p.c4 + cg, v);
+                    st_stream_f4(reinterpret_cast<float4*>(p.out2) + pix * p.c4 + cg, vm);
                 } else {
-                    reinterpret_cast<float4*>(p.out)[pix * p.c4 + cg] = vm;   // sn == 1 unless only the modulated copy is wanted
+                    st_stream_f4(reinterpret_cast<float4*>(p.out) + pix * p.c4 + cg, vm);   // sn == 1 unless only the modulated copy is wanted
                 }
             }
         }
@@ -176,10 +183,10 @@ extern "C" int rick_blur_nhwc(void* out, const void* x, const float* taps, int b
     }
     p.strips_x = (int)ceil_div(p.out_w, TX), p.strips_y = (int)ceil_div(p.out_h, TY);
     const long long total = (long long)batch * p.strips_y * p.strips_x * p.c4;
-    long long blocks = ceil_div(total, 256);
-    const long long cap = (long long)kNumSMs * 32;
+    long long blocks = ceil_div(total, 128);
+    const long long cap = (long long)kNumSMs * 48;
     if (blocks > cap) blocks = cap;
-    blur_nhwc_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    blur_nhwc_kernel<<<(unsigned)blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
     RICK_CHECK_LAUNCH();
     return RICK_OK;
 }
