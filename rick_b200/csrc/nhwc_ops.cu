@@ -33,7 +33,6 @@ struct BlurParams {
 };
 
 constexpr int TX = 2;     // output columns per thread
-constexpr int TY = 16;    // output rows a thread marches down
 
 __device__ __forceinline__ float4 f4_fma(float4 a, float w, float4 acc) {
     acc.x = fmaf(a.x, w, acc.x), acc.y = fmaf(a.y, w, acc.y), acc.z = fmaf(a.z, w, acc.z), acc.w = fmaf(a.w, w, acc.w);
@@ -43,6 +42,7 @@ __device__ __forceinline__ float4 f4_fma(float4 a, float w, float4 acc) {
 // Thread = one float4 channel group x TX output columns, marching down TY output rows with a ring of 5 input rows in
 // registers: while output row dy is computed from rows dy..dy+3, the loads of row dy+4 are already in flight
 // (software prefetch), so each warp keeps >= (TX+3) x 512 B outstanding.  128-thread CTAs, 3 per SM.
+template <int TY>   // output rows a thread marches down (16 for large problems, 4 when parallelism is short)
 __global__ void __launch_bounds__(128, 3) blur_nhwc_kernel(BlurParams p) {
     __shared__ float s_taps[16];
     if (threadIdx.x < 16) {   // out[y] = sum_t in[y + t - pad0] * k[3 - t]  (true convolution, as upfirdn2d)
@@ -181,12 +181,17 @@ extern "C" int rick_blur_nhwc(void* out, const void* x, const float* taps, int b
             (p.s_next && !aligned_to(p.s_next, 16)) || (p.out2 && !aligned_to(p.out2, 16)))
             return RICK_ERR_ALIGNMENT;
     }
-    p.strips_x = (int)ceil_div(p.out_w, TX), p.strips_y = (int)ceil_div(p.out_h, TY);
+    // long row marches amortise the 3-row halo but serialise; use them only when there are >= 8 waves of CTAs anyway
+    p.strips_x = (int)ceil_div(p.out_w, TX);
+    const long long threads16 = (long long)batch * ceil_div(p.out_h, 16) * p.strips_x * p.c4;
+    const int ty = threads16 >= (long long)kNumSMs * 3 * 128 * 8 ? 16 : 4;
+    p.strips_y = (int)ceil_div(p.out_h, ty);
     const long long total = (long long)batch * p.strips_y * p.strips_x * p.c4;
     long long blocks = ceil_div(total, 128);
     const long long cap = (long long)kNumSMs * 48;
     if (blocks > cap) blocks = cap;
-    blur_nhwc_kernel<<<(unsigned)blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    if (ty == 16) blur_nhwc_kernel<16><<<(unsigned)blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    else blur_nhwc_kernel<4><<<(unsigned)blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
     RICK_CHECK_LAUNCH();
     return RICK_OK;
 }

@@ -27,7 +27,13 @@ ncu)
       python -u bench.py --steps 2 --warmup 3 --no-cpu-baseline --quick --cuda-profiler ${NCU_BENCH_ARGS:---mode eager} \
       > gpurun_out/ncu_bench${NCU_TAG}.log 2>&1
   echo "ncu launches rc=$?"
-  timeout 300 ncu --set full --clock-control none --import-source on -k regex:'upfirdn2d_tiled|bias_act' -c 14 \
+  timeout 300 ncu --set full --clock-control none --import-source on \
+      -k regex:'upfirdn2d_tiled|bias_act|blur_nhwc|conv_tc' -s 9 -c 9 \
+      -o gpurun_out/prof_ops python -u scripts/prof_ops.py > gpurun_out/ncu_ops.log 2>&1
+  echo "ncu ops rc=$?" ;;
+ncuops)
+  timeout 300 ncu --set full --clock-control none --import-source on \
+      -k regex:'upfirdn2d_tiled|bias_act|blur_nhwc|conv_tc' -s 9 -c 9 \
       -o gpurun_out/prof_ops python -u scripts/prof_ops.py > gpurun_out/ncu_ops.log 2>&1
   echo "ncu ops rc=$?" ;;
 esac

@@ -1,7 +1,8 @@
-"""Tiny driver for ncu captures of the memory-bound kernels at the BASELINE op-sweep shapes."""
-import sys
+"""Tiny driver for ncu captures of this package's kernels at the BASELINE op-sweep / sample-generation shapes."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
+from rick_b200 import conv_tc as ct
 from rick_b200 import op
 
 dev = "cuda"
@@ -9,16 +10,23 @@ t = torch.tensor([1., 3., 3., 1.], device=dev)
 taps4, taps1 = torch.outer(t, t) / 16, torch.outer(t, t) / 64
 x = torch.randn(32, 512, 128, 128, device=dev)
 b = torch.randn(512, device=dev)
-for _ in range(3):
+xn = torch.randn(32, 129, 129, 512, device=dev)
+xc = torch.randn(64, 64, 64, 512, device=dev)
+wt = torch.randn(9, 512, 512, device=dev) / 68.0
+geom = ct.geom_conv(64, 64, 64, 512, 512, 3, 1, 1)
+geomT = ct.geom_conv_transpose_s2(64, 32, 32, 512, 512)
+xt = torch.randn(64, 32, 32, 512, device=dev)
+for _ in range(2):
     y = op.upfirdn2d(x, taps4, up=2, pad=(2, 1))          # (32,512,256,256)
-    z = op.upfirdn2d(x, taps1, pad=(2, 2))                # D blur
+    z = op.upfirdn2d(x, taps1, pad=(2, 2))                # D blur, NCHW
     d = op.upfirdn2d(x, taps1, down=2, pad=(1, 1))
     xr = x.clone().requires_grad_(True)
     br = b.clone().requires_grad_(True)
     a = op.fused_leaky_relu(xr, br)
     a.backward(torch.ones_like(a))
-xb = torch.randn(32, 512, 129, 129, device=dev)
-for _ in range(3):
-    w = op.upfirdn2d(xb, taps4, pad=(1, 1))
+    w = ct.blur_nhwc(xn, taps4, (1, 1))
+    c1 = ct.conv_tc_nhwc(xc, wt, geom)
+    c2 = ct.conv_tc_nhwc(xt, wt, geomT)
+    del y, z, d, a, w, c1, c2
 torch.cuda.synchronize()
 print("ok")
