@@ -52,13 +52,16 @@ struct PhaseDev {
     int dy[9], dx[9], widx[9];
     int out_y0, out_x0, rows, cols;
     int tiles_y, tiles_x, tile_begin;   // tile_begin: first (pixel-)tile index of this phase
+    // pixel tile of this phase: tw x th pixels of nb samples (any sizes, tw*th*nb <= 256); the MMA runs over
+    // n_mma = roundup16(tw*th*nb) columns, the surplus columns are never stored
+    int tw, th, nb, n_mma, box_bytes;
+    unsigned inv_tw, inv_twth;          // ceil(2^16 / d): exact floor(n / d) for n < 256, d <= 256
 };
 
 struct ConvDev {
     int batch, cout, out_h, out_w, in_stride, out_stride;
     int n_phases;
     PhaseDev phase[4];
-    int log_tw, log_th, log_nb, n_tile;
     int cout_tiles, kblocks, pixel_tiles, total_tiles;
     float* out;
     float* out2;
@@ -88,19 +91,19 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvDev& p, int t) {
     r -= bt * per_img;
     c.phase = ph;
     c.cout0 = ct * kBlockM;
-    c.b0 = bt << p.log_nb;
-    c.y0 = (r / P.tiles_x) << p.log_th;
-    c.x0 = (r % P.tiles_x) << p.log_tw;
+    c.b0 = bt * P.nb;
+    c.y0 = (r / P.tiles_x) * P.th;
+    c.x0 = (r % P.tiles_x) * P.tw;
     return c;
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
-               const __grid_constant__ ConvDev p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x0,
+               const __grid_constant__ CUtensorMap tmap_x1, const __grid_constant__ CUtensorMap tmap_x2,
+               const __grid_constant__ CUtensorMap tmap_x3, const __grid_constant__ ConvDev p) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128-byte swizzle pattern
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int b_bytes = p.n_tile * kBlockK * 4;
     const int stage_bytes = kABytes + kMaxN * kBlockK * 4;      // fixed stride keeps every tile base 1024-aligned
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
     uint64_t* empty_bar = full_bar + kStages;
@@ -113,7 +116,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&tmap_w);
-        tc::tma_prefetch_desc(&tmap_x);
+        tc::tma_prefetch_desc(&tmap_x0);
         for (int s = 0; s < kStages; ++s) {
             tc::mbar_init(&full_bar[s], 1);
             tc::mbar_init(&empty_bar[s], 1);
@@ -140,6 +143,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 const TileCoord c = decode_tile(p, t);
                 const PhaseDev& P = p.phase[c.phase];
+                const CUtensorMap* tmap_x = c.phase == 0 ? &tmap_x0 : (c.phase == 1 ? &tmap_x1 : (c.phase == 2 ? &tmap_x2 : &tmap_x3));
                 for (int tap = 0; tap < P.n_taps; ++tap) {
                     const int gx = c.x0 * p.in_stride + P.dx[tap];
                     const int gy = c.y0 * p.in_stride + P.dy[tap];
@@ -148,21 +152,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                         tc::mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
                         uint8_t* a_dst = smem + s * stage_bytes;
                         uint8_t* b_dst = a_dst + kABytes;
-                        tc::mbar_arrive_expect_tx(&full_bar[s], kABytes + b_bytes);
+                        tc::mbar_arrive_expect_tx(&full_bar[s], kABytes + P.box_bytes);
                         tc::tma_load_3d(a_dst, &tmap_w, &full_bar[s], kb * kBlockK, c.cout0, P.widx[tap]);
-                        tc::tma_load_4d(b_dst, &tmap_x, &full_bar[s], kb * kBlockK, gx, gy, c.b0);
+                        tc::tma_load_4d(b_dst, tmap_x, &full_bar[s], kb * kBlockK, gx, gy, c.b0);
                     }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================================================== MMA issuer
-        const uint32_t idesc = tc::umma_idesc_tf32(kBlockM, p.n_tile);
         uint32_t it = 0;
         uint32_t tile_n = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_n) {
             const TileCoord c = decode_tile(p, t);
             const int n_kblocks = p.phase[c.phase].n_taps * p.kblocks;
+            const uint32_t idesc = tc::umma_idesc_tf32(kBlockM, p.phase[c.phase].n_mma);
             const uint32_t acc = tile_n & 1;
             tc::mbar_wait(&tmem_empty[acc], ((tile_n >> 1) & 1) ^ 1);
             tc::tc_fence_after_sync();
@@ -190,7 +194,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         // ===================================================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
         const int quarter = warp & 3;
         uint32_t tile_n = 0;
-        const int tw_mask = (1 << p.log_tw) - 1, th_mask = (1 << p.log_th) - 1;
         const float nw = p.noise ? __ldg(p.noise_w) : 0.f;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_n) {
             const TileCoord c = decode_tile(p, t);
@@ -203,16 +206,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             const uint32_t taddr = tmem_base + acc * kMaxN + (static_cast<uint32_t>(quarter * 32) << 16);
             int cur_b = -1;
             float dm = 1.f, sn = 1.f;
-            for (int n0 = 0; n0 < p.n_tile; n0 += 32) {
+            const int n_valid = P.tw * P.th * P.nb;
+            for (int n0 = 0; n0 < n_valid; n0 += 32) {
                 uint32_t v[32];
                 tc::tmem_ld_32x32b_x32(taddr + n0, v);
                 tc::tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int n = n0 + j;
-                    const int m_y = c.y0 + ((n >> p.log_tw) & th_mask);
-                    const int m_x = c.x0 + (n & tw_mask);
-                    const int b = c.b0 + (n >> (p.log_tw + p.log_th));
+                    if (n >= n_valid) break;
+                    const int bi = (int)((unsigned)n * P.inv_twth >> 16);            // n / (tw*th)
+                    const int rem = n - bi * (P.tw * P.th);
+                    const int yi = (int)((unsigned)rem * P.inv_tw >> 16);             // rem / tw
+                    const int m_y = c.y0 + yi;
+                    const int m_x = c.x0 + (rem - yi * P.tw);
+                    const int b = c.b0 + bi;
                     if (m_y >= P.rows || m_x >= P.cols || b >= p.batch) continue;
                     if (b != cur_b) {
                         cur_b = b;
@@ -248,12 +256,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     }
 }
 
-int ilog2_exact(int v) {
-    int l = 0;
-    while ((1 << l) < v) ++l;
-    return (1 << l) == v ? l : -1;
-}
-
 }  // namespace
 }  // namespace rick
 
@@ -269,30 +271,43 @@ extern "C" int rick_conv_tc(void* out, const void* xm, const void* wt, const ric
     EncodeTiledFn encode = get_encode_tiled();
     if (!encode) return RICK_ERR_UNSUPPORTED;
 
-    // ---- pixel tile: tw x th x nb pixels (powers of two, product <= 256, multiple of 16) ----
-    int max_rows = 0, max_cols = 0;
+    // ---- pixel tile per phase: tw x th pixels of nb samples, tw*th*nb <= 256, chosen to minimise the padded MMA work
+    //      ceil(cols/tw) * ceil(rows/th) * ceil(batch/nb) * roundup16(tw*th*nb); ties go to the wider tile.
+    //      (33x33 -> 17x11 tiles, 65x65 -> 17x13, 129x129 -> 43x5: the (2H+1)^2 outputs of the transposed conv) ----
     for (int i = 0; i < g->n_phases; ++i) {
         if (g->phase[i].n_taps < 1 || g->phase[i].n_taps > 9) return RICK_ERR_INVALID_ARGUMENT;
-        if (g->phase[i].rows > max_rows) max_rows = g->phase[i].rows;
-        if (g->phase[i].cols > max_cols) max_cols = g->phase[i].cols;
+        if (g->phase[i].rows < 1 || g->phase[i].cols < 1) return RICK_ERR_INVALID_ARGUMENT;
     }
-    if (max_rows < 1 || max_cols < 1) return RICK_ERR_INVALID_ARGUMENT;
-    auto pow2_ceil = [](int v) { int r = 1; while (r < v) r <<= 1; return r; };
-    int tw = pow2_ceil(max_cols);
-    if (tw > 32) tw = 32;
-    if (g->in_stride == 2 && tw > 32) tw = 32;
-    int th = pow2_ceil(max_rows);
-    if (th > kMaxN / tw) th = kMaxN / tw;
-    int nb = 1;
-    while (tw * th * nb * 2 <= kMaxN && nb < pow2_ceil(g->batch)) nb <<= 1;
-    int n_tile = tw * th * nb;
-    while (n_tile < 16) { nb <<= 1; n_tile <<= 1; }     // UMMA needs N % 16 == 0 at M = 128
-    if (tw * g->in_stride > 256 || th * g->in_stride > 256) return RICK_ERR_UNSUPPORTED;
+    auto choose_tile = [&](int rows, int cols, int& tw, int& th, int& nb) {
+        double best = -1.0;
+        const int max_side = 256 / g->in_stride;               // TMA box extent (in input pixels) must be <= 256
+        for (int kx = 1; kx <= cols; ++kx) {                   // kx tiles across, balanced widths
+            const int w_ = (int)ceil_div(cols, kx);
+            if (w_ > max_side || w_ > kMaxN) continue;
+            int hmax = kMaxN / w_;
+            if (hmax > rows) hmax = rows;
+            if (hmax > max_side) hmax = max_side;
+            if (hmax < 1) continue;
+            const int ky = (int)ceil_div(rows, hmax);
+            const int h_ = (int)ceil_div(rows, ky);            // balanced heights
+            int n_ = 1;
+            if (w_ >= cols && h_ >= rows) {                    // whole image fits: stack samples
+                n_ = kMaxN / (w_ * h_);
+                if (n_ > g->batch) n_ = g->batch;
+                if (n_ < 1) n_ = 1;
+                n_ = (int)ceil_div(g->batch, ceil_div(g->batch, n_));
+            }
+            const int n_mma = ((w_ * h_ * n_ + 15) / 16) * 16;
+            // padded MMA work, with a mild penalty on narrow tiles (weights are re-streamed per tile)
+            const double cost = (double)(ceil_div(cols, w_) * ceil_div(rows, h_) * ceil_div(g->batch, n_)) *
+                                (n_mma + 32.0);
+            if (best < 0 || cost < best - 1e-9) best = cost, tw = w_, th = h_, nb = n_;
+        }
+    };
 
     ConvDev p{};
     p.batch = g->batch, p.cout = g->cout, p.out_h = g->out_h, p.out_w = g->out_w;
     p.in_stride = g->in_stride, p.out_stride = g->out_stride, p.n_phases = g->n_phases;
-    p.log_tw = ilog2_exact(tw), p.log_th = ilog2_exact(th), p.log_nb = ilog2_exact(nb), p.n_tile = n_tile;
     p.cout_tiles = g->cout / kBlockM, p.kblocks = g->cin / kBlockK;
     int tiles = 0;
     for (int i = 0; i < g->n_phases; ++i) {
@@ -307,6 +322,13 @@ extern "C" int rick_conv_tc(void* out, const void* xm, const void* wt, const ric
         if ((Q.rows - 1) * g->out_stride + Q.out_y0 >= g->out_h || (Q.cols - 1) * g->out_stride + Q.out_x0 >= g->out_w ||
             Q.out_y0 < 0 || Q.out_x0 < 0)
             return RICK_ERR_INVALID_ARGUMENT;
+        int tw = 1, th = 1, nb = 1;
+        choose_tile(Q.rows, Q.cols, tw, th, nb);
+        P.tw = tw, P.th = th, P.nb = nb;
+        P.n_mma = ((tw * th * nb + 15) / 16) * 16;
+        P.box_bytes = tw * th * nb * kBlockK * 4;
+        P.inv_tw = (65536u + tw - 1) / tw;
+        P.inv_twth = (65536u + tw * th - 1) / (tw * th);
         P.tiles_y = (int)ceil_div(Q.rows, th), P.tiles_x = (int)ceil_div(Q.cols, tw);
         P.tile_begin = tiles;
         tiles += P.tiles_y * P.tiles_x * (int)ceil_div(g->batch, nb);
@@ -322,7 +344,7 @@ extern "C" int rick_conv_tc(void* out, const void* xm, const void* wt, const ric
     }
 
     // ---- tensor maps ----
-    CUtensorMap tmap_w, tmap_x;
+    CUtensorMap tmap_w, tmap_x[4];
     {
         cuuint64_t dims[3] = {(cuuint64_t)g->cin, (cuuint64_t)g->cout, (cuuint64_t)g->n_weight_taps};
         cuuint64_t strides[2] = {(cuuint64_t)g->cin * 4, (cuuint64_t)g->cin * g->cout * 4};
@@ -333,14 +355,16 @@ extern "C" int rick_conv_tc(void* out, const void* xm, const void* wt, const ric
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return RICK_ERR_INVALID_ARGUMENT;
     }
-    {
+    for (int i = 0; i < 4; ++i) {
+        const PhaseDev& P = p.phase[i < g->n_phases ? i : 0];
         cuuint64_t dims[4] = {(cuuint64_t)g->cin, (cuuint64_t)g->in_w, (cuuint64_t)g->in_h, (cuuint64_t)g->batch};
         cuuint64_t strides[3] = {(cuuint64_t)g->cin * 4, (cuuint64_t)g->cin * g->in_w * 4,
                                  (cuuint64_t)g->cin * g->in_w * g->in_h * 4};
         // with a traversal stride s the box spans tw*s input pixels and delivers ceil(box/s) = tw of them
-        cuuint32_t box[4] = {kBlockK, (cuuint32_t)(tw * g->in_stride), (cuuint32_t)(th * g->in_stride), (cuuint32_t)nb};
+        cuuint32_t box[4] = {kBlockK, (cuuint32_t)(P.tw * g->in_stride), (cuuint32_t)(P.th * g->in_stride),
+                             (cuuint32_t)P.nb};
         cuuint32_t estr[4] = {1, (cuuint32_t)g->in_stride, (cuuint32_t)g->in_stride, 1};
-        if (encode(&tmap_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(xm), dims, strides, box, estr,
+        if (encode(&tmap_x[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(xm), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return RICK_ERR_INVALID_ARGUMENT;
@@ -358,7 +382,8 @@ extern "C" int rick_conv_tc(void* out, const void* xm, const void* wt, const ric
         }
     }
     int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
-    conv_tc_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmap_w, tmap_x, p);
+    conv_tc_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmap_w, tmap_x[0], tmap_x[1], tmap_x[2],
+                                                                              tmap_x[3], p);
     RICK_CHECK_LAUNCH();
     return RICK_OK;
 }
