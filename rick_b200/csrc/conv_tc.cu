@@ -110,6 +110,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     uint64_t* tmem_full = empty_bar + kStages;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    int* ep_pix = reinterpret_cast<int*>(tmem_base_slot + 4);                 // [2][256] output pixel index or -1
+    float* ep_nz = reinterpret_cast<float*>(ep_pix + 2 * kMaxN);              // [2][256] noise_w * noise
+    short* ep_b = reinterpret_cast<short*>(ep_nz + 2 * kMaxN);                // [2][256] sample index
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -192,53 +195,81 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         }
     } else {
         // ===================================================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
+        // Per tile, stage A (overlaps the MMAs of this tile): the 128 epilogue threads decode the tile's <= 256 columns
+        // once -- output pixel index (or -1), noise_w * noise, sample index -- into a double-buffered shared table.
+        // Stage B then costs a broadcast LDS + FMA + coalesced 128 B stores per column: no per-column global load and
+        // no per-thread index arithmetic between the tcgen05.ld and the stores.
         const int quarter = warp & 3;
+        const int e = threadIdx.x - 64;
         uint32_t tile_n = 0;
         const float nw = p.noise ? __ldg(p.noise_w) : 0.f;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_n) {
             const TileCoord c = decode_tile(p, t);
             const PhaseDev& P = p.phase[c.phase];
             const uint32_t acc = tile_n & 1;
+            int* pixtab = ep_pix + acc * kMaxN;
+            float* nztab = ep_nz + acc * kMaxN;
+            short* btab = ep_b + acc * kMaxN;
+            const int n_valid = P.tw * P.th * P.nb;
+            for (int n = e; n < kMaxN; n += 128) {
+                int pix = -1, bb = 0;
+                float nz = 0.f;
+                if (n < n_valid) {
+                    const int bi = (int)((unsigned)n * P.inv_twth >> 16);            // n / (tw*th)
+                    const int rem = n - bi * (P.tw * P.th);
+                    const int yi = (int)((unsigned)rem * P.inv_tw >> 16);             // rem / tw
+                    const int m_y = c.y0 + yi, m_x = c.x0 + (rem - yi * P.tw), b = c.b0 + bi;
+                    if (m_y < P.rows && m_x < P.cols && b < p.batch) {
+                        pix = (b * p.out_h + m_y * p.out_stride + P.out_y0) * p.out_w + m_x * p.out_stride + P.out_x0;
+                        if (p.noise) nz = nw * __ldg(p.noise + pix);
+                        bb = b;
+                    }
+                }
+                pixtab[n] = pix, nztab[n] = nz, btab[n] = (short)bb;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+
             const int co = c.cout0 + quarter * 32 + lane;
             const float bias = p.bias ? __ldg(p.bias + co) : 0.f;
+            int cur_b = c.b0 < p.batch ? c.b0 : p.batch - 1;
+            float dm = p.demod ? __ldg(p.demod + (size_t)cur_b * p.cout + co) : 1.f;
+            float sn = p.s_next ? __ldg(p.s_next + (size_t)cur_b * p.cout + co) : 1.f;
             tc::mbar_wait(&tmem_full[acc], (tile_n >> 1) & 1);
             tc::tc_fence_after_sync();
             const uint32_t taddr = tmem_base + acc * kMaxN + (static_cast<uint32_t>(quarter * 32) << 16);
-            int cur_b = -1;
-            float dm = 1.f, sn = 1.f;
-            const int n_valid = P.tw * P.th * P.nb;
+            float* const outp = p.out + co;
+            float* const out2p = p.out2 ? p.out2 + co : nullptr;
             for (int n0 = 0; n0 < n_valid; n0 += 32) {
                 uint32_t v[32];
                 tc::tmem_ld_32x32b_x32(taddr + n0, v);
                 tc::tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int n = n0 + j;
-                    if (n >= n_valid) break;
-                    const int bi = (int)((unsigned)n * P.inv_twth >> 16);            // n / (tw*th)
-                    const int rem = n - bi * (P.tw * P.th);
-                    const int yi = (int)((unsigned)rem * P.inv_tw >> 16);             // rem / tw
-                    const int m_y = c.y0 + yi;
-                    const int m_x = c.x0 + (rem - yi * P.tw);
-                    const int b = c.b0 + bi;
-                    if (m_y >= P.rows || m_x >= P.cols || b >= p.batch) continue;
-                    if (b != cur_b) {
-                        cur_b = b;
-                        if (p.demod) dm = __ldg(p.demod + (size_t)b * p.cout + co);
-                        if (p.s_next) sn = __ldg(p.s_next + (size_t)b * p.cout + co);
-                    }
-                    const int oy = m_y * p.out_stride + P.out_y0;
-                    const int ox = m_x * p.out_stride + P.out_x0;
-                    const size_t pix = ((size_t)b * p.out_h + oy) * p.out_w + ox;
-                    float r = __uint_as_float(v[j]) * dm;
-                    if (p.noise) r = fmaf(nw, __ldg(p.noise + pix), r);
-                    r += bias;
-                    if (p.act) r = (r > 0.f ? r : r * p.alpha) * p.scale;
-                    if (p.out2) {
-                        p.out[pix * p.cout + co] = r;
-                        p.out2[pix * p.cout + co] = r * sn;
-                    } else {
-                        p.out[pix * p.cout + co] = r * sn;     // sn == 1 unless only the modulated copy is wanted
+                for (int j4 = 0; j4 < 32; j4 += 4) {
+                    const int4 pq = *reinterpret_cast<const int4*>(pixtab + n0 + j4);
+                    const float4 nq = *reinterpret_cast<const float4*>(nztab + n0 + j4);
+                    const int pixs[4] = {pq.x, pq.y, pq.z, pq.w};
+                    const float nzs[4] = {nq.x, nq.y, nq.z, nq.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int pix = pixs[k];
+                        if (pix < 0) continue;
+                        if (P.nb > 1) {                       // several samples per tile (small feature maps only)
+                            const int b = btab[n0 + j4 + k];
+                            if (b != cur_b) {
+                                cur_b = b;
+                                if (p.demod) dm = __ldg(p.demod + (size_t)b * p.cout + co);
+                                if (p.s_next) sn = __ldg(p.s_next + (size_t)b * p.cout + co);
+                            }
+                        }
+                        float r = fmaf(__uint_as_float(v[j4 + k]), dm, nzs[k]) + bias;
+                        if (p.act) r = (r > 0.f ? r : r * p.alpha) * p.scale;
+                        const size_t off = (size_t)pix * p.cout;
+                        if (out2p) {
+                            outp[off] = r;
+                            out2p[off] = r * sn;
+                        } else {
+                            outp[off] = r * sn;                // sn == 1 unless only the modulated copy is wanted
+                        }
                     }
                 }
             }
@@ -268,6 +299,7 @@ extern "C" int rick_conv_tc(void* out, const void* xm, const void* wt, const ric
     if (g->cout % kBlockM != 0 || g->cin % kBlockK != 0) return RICK_ERR_UNSUPPORTED;
     if (g->in_stride < 1 || g->in_stride > 2 || g->out_stride < 1 || g->out_stride > 2) return RICK_ERR_UNSUPPORTED;
     if (!aligned_to(out, 16) || !aligned_to(xm, 16) || !aligned_to(wt, 16)) return RICK_ERR_ALIGNMENT;
+    if ((long long)g->batch * g->out_h * g->out_w > 0x7fffffffLL) return RICK_ERR_OVERFLOW;   // 32-bit pixel indices
     EncodeTiledFn encode = get_encode_tiled();
     if (!encode) return RICK_ERR_UNSUPPORTED;
 
@@ -371,7 +403,7 @@ extern "C" int rick_conv_tc(void* out, const void* xm, const void* wt, const ric
     }
 
     const int stage_bytes = kABytes + kMaxN * kBlockK * 4;
-    const size_t smem = 1024 + (size_t)kStages * stage_bytes + 256;
+    const size_t smem = 1024 + (size_t)kStages * stage_bytes + 256 + 2 * kMaxN * (4 + 4 + 2);
     {   // once per device; kept out of later calls so that launches can be recorded into CUDA graphs
         static bool attr_done[64] = {};
         int dev = 0;
