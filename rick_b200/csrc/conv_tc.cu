@@ -147,6 +147,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                 const TileCoord c = decode_tile(p, t);
                 const PhaseDev& P = p.phase[c.phase];
                 const CUtensorMap* tmap_x = c.phase == 0 ? &tmap_x0 : (c.phase == 1 ? &tmap_x1 : (c.phase == 2 ? &tmap_x2 : &tmap_x3));
+                // Shallow-K layers (Cin <= 256) finish a tile in ~10 us, too little for a 4-stage ring to cover the DRAM
+                // latency of rows that no tile has touched yet: pull the NEXT tile's activation rows into L2 now (one
+                // box per distinct dy; the dx-shifted boxes overlap it).
+                if (p.kblocks <= 8 && t + (int)gridDim.x < p.total_tiles) {
+                    const TileCoord cn = decode_tile(p, t + gridDim.x);
+                    const PhaseDev& Pn = p.phase[cn.phase];
+                    const CUtensorMap* tmap_n = cn.phase == 0 ? &tmap_x0 : (cn.phase == 1 ? &tmap_x1 : (cn.phase == 2 ? &tmap_x2 : &tmap_x3));
+                    for (int tap = 0; tap < Pn.n_taps; ++tap) {
+                        bool seen = false;
+                        for (int q = 0; q < tap; ++q) seen |= (Pn.dy[q] == Pn.dy[tap]);
+                        if (seen) continue;
+                        for (int kb = 0; kb < p.kblocks; ++kb)
+                            tc::tma_prefetch_l2_4d(tmap_n, kb * kBlockK, cn.x0 * p.in_stride + Pn.dx[tap],
+                                                   cn.y0 * p.in_stride + Pn.dy[tap], cn.b0);
+                    }
+                }
                 for (int tap = 0; tap < P.n_taps; ++tap) {
                     const int gx = c.x0 * p.in_stride + P.dx[tap];
                     const int gy = c.y0 * p.in_stride + P.dy[tap];
