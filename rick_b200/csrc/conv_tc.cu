@@ -97,6 +97,47 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvDev& p, int t) {
     return c;
 }
 
+// Stage B of the epilogue for one 32-column chunk: everything per column is a table read, a handful of FP ops and one
+// or two coalesced stores.  Flags that are uniform per launch are template parameters so the body stays ~12 SASS
+// instructions per column (the first version spent ~70 and was bound by instruction issue / I-cache misses).
+template <bool ACT, bool DUAL, bool MULTI_B>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const int* __restrict__ offtab,
+                                               const float* __restrict__ nztab, const short* __restrict__ btab,
+                                               float* __restrict__ outp, long long out2_delta, const ConvDev& p, int co,
+                                               float bias, float alpha, float scale, float& dm, float& sn, int& cur_b) {
+#pragma unroll 8
+    for (int j4 = 0; j4 < 32; j4 += 4) {
+        const int4 oq = *reinterpret_cast<const int4*>(offtab + j4);
+        const float4 nq = *reinterpret_cast<const float4*>(nztab + j4);
+        const int offs[4] = {oq.x, oq.y, oq.z, oq.w};
+        const float nzs[4] = {nq.x, nq.y, nq.z, nq.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int off = offs[k];                       // element offset of (pixel, channel 0), or -1
+            if (MULTI_B) {                                 // several samples per tile (small feature maps only)
+                const int b = btab[j4 + k];
+                if (off >= 0 && b != cur_b) {
+                    cur_b = b;
+                    if (p.demod) dm = __ldg(p.demod + (size_t)b * p.cout + co);
+                    if (p.s_next) sn = __ldg(p.s_next + (size_t)b * p.cout + co);
+                }
+            }
+            float r = fmaf(__uint_as_float(v[j4 + k]), dm, nzs[k]) + bias;
+            if (ACT) r = (r > 0.f ? r : r * alpha) * scale;
+            if (off >= 0) {
+                float* dst = outp + off;
+                if (DUAL) {
+                    dst[0] = r;
+                    dst[out2_delta] = r * sn;
+                } else {
+                    dst[0] = r * sn;                       // sn == 1 unless only the modulated copy is wanted
+                }
+            }
+        }
+    }
+}
+
+template <bool ACT, bool DUAL>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x0,
                const __grid_constant__ CUtensorMap tmap_x1, const __grid_constant__ CUtensorMap tmap_x2,
@@ -110,9 +151,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     uint64_t* tmem_full = empty_bar + kStages;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    int* ep_pix = reinterpret_cast<int*>(tmem_base_slot + 4);                 // [2][256] output pixel index or -1
-    float* ep_nz = reinterpret_cast<float*>(ep_pix + 2 * kMaxN);              // [2][256] noise_w * noise
-    short* ep_b = reinterpret_cast<short*>(ep_nz + 2 * kMaxN);                // [2][256] sample index
+    // epilogue column tables (static shared memory so that reads compile to LDS, not generic loads)
+    __shared__ __align__(16) int ep_pix[2 * kMaxN];      // element offset of (pixel, channel 0) or -1
+    __shared__ __align__(16) float ep_nz[2 * kMaxN];     // noise_w * noise
+    __shared__ short ep_b[2 * kMaxN];                    // sample index
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -219,6 +261,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         const int e = threadIdx.x - 64;
         uint32_t tile_n = 0;
         const float nw = p.noise ? __ldg(p.noise_w) : 0.f;
+        const float alpha = p.alpha, scale = p.scale;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_n) {
             const TileCoord c = decode_tile(p, t);
             const PhaseDev& P = p.phase[c.phase];
@@ -239,6 +282,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                         pix = (b * p.out_h + m_y * p.out_stride + P.out_y0) * p.out_w + m_x * p.out_stride + P.out_x0;
                         if (p.noise) nz = nw * __ldg(p.noise + pix);
                         bb = b;
+                        pix *= p.cout;                                     // element offset (host guarantees < 2^31)
                     }
                 }
                 pixtab[n] = pix, nztab[n] = nz, btab[n] = (short)bb;
@@ -254,40 +298,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             tc::tc_fence_after_sync();
             const uint32_t taddr = tmem_base + acc * kMaxN + (static_cast<uint32_t>(quarter * 32) << 16);
             float* const outp = p.out + co;
-            float* const out2p = p.out2 ? p.out2 + co : nullptr;
+            const long long out2_delta = DUAL ? (p.out2 - p.out) : 0;
             for (int n0 = 0; n0 < n_valid; n0 += 32) {
                 uint32_t v[32];
                 tc::tmem_ld_32x32b_x32(taddr + n0, v);
                 tc::tmem_ld_wait();
-#pragma unroll
-                for (int j4 = 0; j4 < 32; j4 += 4) {
-                    const int4 pq = *reinterpret_cast<const int4*>(pixtab + n0 + j4);
-                    const float4 nq = *reinterpret_cast<const float4*>(nztab + n0 + j4);
-                    const int pixs[4] = {pq.x, pq.y, pq.z, pq.w};
-                    const float nzs[4] = {nq.x, nq.y, nq.z, nq.w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int pix = pixs[k];
-                        if (pix < 0) continue;
-                        if (P.nb > 1) {                       // several samples per tile (small feature maps only)
-                            const int b = btab[n0 + j4 + k];
-                            if (b != cur_b) {
-                                cur_b = b;
-                                if (p.demod) dm = __ldg(p.demod + (size_t)b * p.cout + co);
-                                if (p.s_next) sn = __ldg(p.s_next + (size_t)b * p.cout + co);
-                            }
-                        }
-                        float r = fmaf(__uint_as_float(v[j4 + k]), dm, nzs[k]) + bias;
-                        if (p.act) r = (r > 0.f ? r : r * p.alpha) * p.scale;
-                        const size_t off = (size_t)pix * p.cout;
-                        if (out2p) {
-                            outp[off] = r;
-                            out2p[off] = r * sn;
-                        } else {
-                            outp[off] = r * sn;                // sn == 1 unless only the modulated copy is wanted
-                        }
-                    }
-                }
+                if (P.nb > 1)
+                    epilogue_chunk<ACT, DUAL, true>(v, pixtab + n0, nztab + n0, btab + n0, outp, out2_delta, p, co, bias,
+                                                    alpha, scale, dm, sn, cur_b);
+                else
+                    epilogue_chunk<ACT, DUAL, false>(v, pixtab + n0, nztab + n0, btab + n0, outp, out2_delta, p, co, bias,
+                                                     alpha, scale, dm, sn, cur_b);
             }
             tc::tc_fence_before_sync();
             __syncwarp();
@@ -315,7 +336,7 @@ extern "C" int rick_conv_tc(void* out, const void* xm, const void* wt, const ric
     if (g->cout % kBlockM != 0 || g->cin % kBlockK != 0) return RICK_ERR_UNSUPPORTED;
     if (g->in_stride < 1 || g->in_stride > 2 || g->out_stride < 1 || g->out_stride > 2) return RICK_ERR_UNSUPPORTED;
     if (!aligned_to(out, 16) || !aligned_to(xm, 16) || !aligned_to(wt, 16)) return RICK_ERR_ALIGNMENT;
-    if ((long long)g->batch * g->out_h * g->out_w > 0x7fffffffLL) return RICK_ERR_OVERFLOW;   // 32-bit pixel indices
+    if ((long long)g->batch * g->out_h * g->out_w * g->cout > 0x7fffffffLL) return RICK_ERR_OVERFLOW;   // 32-bit offsets
     EncodeTiledFn encode = get_encode_tiled();
     if (!encode) return RICK_ERR_UNSUPPORTED;
 
@@ -419,19 +440,22 @@ extern "C" int rick_conv_tc(void* out, const void* xm, const void* wt, const ric
     }
 
     const int stage_bytes = kABytes + kMaxN * kBlockK * 4;
-    const size_t smem = 1024 + (size_t)kStages * stage_bytes + 256 + 2 * kMaxN * (4 + 4 + 2);
-    {   // once per device; kept out of later calls so that launches can be recorded into CUDA graphs
-        static bool attr_done[64] = {};
+    const size_t smem = 1024 + (size_t)kStages * stage_bytes + 256;
+    const bool act = p.act != 0, dual = p.out2 != nullptr;
+    auto kernel = act ? (dual ? conv_tc_kernel<true, true> : conv_tc_kernel<true, false>)
+                      : (dual ? conv_tc_kernel<false, true> : conv_tc_kernel<false, false>);
+    {   // once per device and variant; kept out of later calls so that launches can be recorded into CUDA graphs
+        static bool attr_done[64][4] = {};
         int dev = 0;
         RICK_CUDA_TRY(cudaGetDevice(&dev));
-        if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-            RICK_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            if (dev >= 0 && dev < 64) attr_done[dev] = true;
+        const int variant = (act ? 2 : 0) + (dual ? 1 : 0);
+        if (dev < 0 || dev >= 64 || !attr_done[dev][variant]) {
+            RICK_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (dev >= 0 && dev < 64) attr_done[dev][variant] = true;
         }
     }
     int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
-    conv_tc_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmap_w, tmap_x[0], tmap_x[1], tmap_x[2],
-                                                                              tmap_x[3], p);
+    kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmap_w, tmap_x[0], tmap_x[1], tmap_x[2], tmap_x[3], p);
     RICK_CHECK_LAUNCH();
     return RICK_OK;
 }
