@@ -89,9 +89,9 @@ struct Window {  // 1-D footprint of OUTS consecutive outputs (first one at a mu
     static constexpr int size = dmax - dmin + 1;
 };
 
-template <typename T, int UP, int DOWN, int PX, int PY, int OY>
+template <typename T, int UP, int DOWN, int PX, int PY, int OY, int OX>
 __global__ void __launch_bounds__(256) upfirdn2d_tiled(UpfirdnParams p) {
-    constexpr int OX = 4;
+    static_assert(OX % 4 == 0, "outputs per thread in x must allow 128-bit stores");
     using WX = Window<UP, DOWN, PX, OX>;
     using WY = Window<UP, DOWN, PY, OY>;
     constexpr int VEC = (UP == 2) ? 2 : 4;                       // floats per shared-memory load
@@ -201,9 +201,10 @@ __global__ void __launch_bounds__(256) upfirdn2d_tiled(UpfirdnParams p) {
     T* out = static_cast<T*>(p.out) + (plane * p.out_h + oy0) * (long long)p.out_w + ox0;
     const bool full_x = (ox0 + OX <= p.out_w);
     const bool vec_ok = full_x && ((p.out_w & 3) == 0) && (sizeof(T) == 4);
+    const bool fast = vec_ok && (oy0 + OY <= p.out_h);      // whole patch inside the image: no per-row / per-column checks
 #pragma unroll
     for (int oy = 0; oy < OY; ++oy) {
-        if (oy0 + oy >= p.out_h) break;
+        if (!fast && oy0 + oy >= p.out_h) break;
         float acc[OX];
 #pragma unroll
         for (int ox = 0; ox < OX; ++ox) {
@@ -225,7 +226,10 @@ __global__ void __launch_bounds__(256) upfirdn2d_tiled(UpfirdnParams p) {
         }
         T* row = out + (long long)oy * p.out_w;
         if (vec_ok) {
-            st_stream_f4(reinterpret_cast<float4*>(row), make_float4(acc[0], acc[1], acc[2], acc[3]));
+#pragma unroll
+            for (int v4 = 0; v4 < OX; v4 += 4)
+                st_stream_f4(reinterpret_cast<float4*>(row + v4),
+                             make_float4(acc[v4], acc[v4 + 1], acc[v4 + 2], acc[v4 + 3]));
         } else {
 #pragma unroll
             for (int ox = 0; ox < OX; ++ox)
@@ -240,9 +244,8 @@ static int ilog2_ceil(int v) {
     return l;
 }
 
-template <typename T, int UP, int DOWN, int PX, int PY, int OY>
+template <typename T, int UP, int DOWN, int PX, int PY, int OY, int OX = 4>
 static int launch_tiled(UpfirdnParams p, cudaStream_t stream) {
-    constexpr int OX = 4;
     using WX = Window<UP, DOWN, PX, OX>;
     using WY = Window<UP, DOWN, PY, OY>;
     constexpr int VEC = (UP == 2) ? 2 : 4;
@@ -269,7 +272,7 @@ static int launch_tiled(UpfirdnParams p, cudaStream_t stream) {
     const long long blocks = (long long)p.tiles_x * p.tiles_y * ceil_div(p.planes, tpn);
     if (blocks > 0x7fffffffLL) return RICK_ERR_OVERFLOW;
     const size_t smem = (size_t)tpn * plane_floats * sizeof(float);
-    upfirdn2d_tiled<T, UP, DOWN, PX, PY, OY><<<(unsigned)blocks, txn * tyn * tpn, smem, stream>>>(p);
+    upfirdn2d_tiled<T, UP, DOWN, PX, PY, OY, OX><<<(unsigned)blocks, txn * tyn * tpn, smem, stream>>>(p);
     RICK_CHECK_LAUNCH();
     return RICK_OK;
 }
@@ -299,6 +302,8 @@ static int dispatch(UpfirdnParams p, cudaStream_t stream) {
     const int px = floor_mod(p.pad_x0, up), py = floor_mod(p.pad_y0, up);
     if (up == 1 && p.down_x == 1) return launch_tiled<T, 1, 1, 0, 0, 4>(p, stream);
     if (up == 1 && p.down_x == 2) return launch_tiled<T, 1, 2, 0, 0, 2>(p, stream);
+    if (px == 0 && py == 0 && p.out_w >= 256 && sizeof(T) == 4)
+        return launch_tiled<T, 2, 1, 0, 0, 8, 8>(p, stream);      // 8 x 8 outputs per thread: least overhead per output
     if (px == 0 && py == 0) return launch_tiled<T, 2, 1, 0, 0, 8>(p, stream);
     if (px == 1 && py == 0) return launch_tiled<T, 2, 1, 1, 0, 8>(p, stream);
     if (px == 0 && py == 1) return launch_tiled<T, 2, 1, 0, 1, 8>(p, stream);
