@@ -51,7 +51,7 @@ struct PhaseDev {
     int n_taps;
     int dy[9], dx[9], widx[9];
     int out_y0, out_x0, rows, cols;
-    int tiles_y, tiles_x, tile_begin;   // tile_begin: first (pixel-)tile index of this phase
+    int tiles_y, tiles_x, tile_begin;   // tile_begin: first tile index of this phase INSIDE one sample group
     // pixel tile of this phase: tw x th pixels of nb samples (any sizes, tw*th*nb <= 256); the MMA runs over
     // n_mma = roundup16(tw*th*nb) columns, the surplus columns are never stored
     int tw, th, nb, n_mma, box_bytes;
@@ -62,7 +62,7 @@ struct ConvDev {
     int batch, cout, out_h, out_w, in_stride, out_stride;
     int n_phases;
     PhaseDev phase[4];
-    int cout_tiles, kblocks, pixel_tiles, total_tiles;
+    int cout_tiles, kblocks, tiles_per_group, total_tiles;   // sample group = nb samples; all phases share nb
     float* out;
     float* out2;
     const float* demod;
@@ -78,20 +78,22 @@ struct TileCoord {
     int phase, cout0, b0, y0, x0;
 };
 
+// Tile order: cout tile fastest, then the tiles of all phases of one sample group, then the next group.  Keeping the
+// (up to four) polyphase passes over the same samples adjacent in time keeps their input resident in L2 (phase-major
+// order re-read the whole activation tensor from DRAM once per phase: 7x the algorithmic traffic in the first profile).
 __device__ __forceinline__ TileCoord decode_tile(const ConvDev& p, int t) {
     TileCoord c;
     const int ct = t % p.cout_tiles;
     int r = t / p.cout_tiles;
+    const int group = r / p.tiles_per_group;
+    r -= group * p.tiles_per_group;
     int ph = 0;
     while (ph + 1 < p.n_phases && r >= p.phase[ph + 1].tile_begin) ++ph;
     r -= p.phase[ph].tile_begin;
     const PhaseDev& P = p.phase[ph];
-    const int per_img = P.tiles_y * P.tiles_x;
-    const int bt = r / per_img;
-    r -= bt * per_img;
     c.phase = ph;
     c.cout0 = ct * kBlockM;
-    c.b0 = bt * P.nb;
+    c.b0 = group * P.nb;
     c.y0 = (r / P.tiles_x) * P.th;
     c.x0 = (r % P.tiles_x) * P.tw;
     return c;
@@ -378,6 +380,14 @@ extern "C" int rick_conv_tc(void* out, const void* xm, const void* wt, const ric
     p.batch = g->batch, p.cout = g->cout, p.out_h = g->out_h, p.out_w = g->out_w;
     p.in_stride = g->in_stride, p.out_stride = g->out_stride, p.n_phases = g->n_phases;
     p.cout_tiles = g->cout / kBlockM, p.kblocks = g->cin / kBlockK;
+    int nb_common = 1 << 30;
+    int ptw[4], pth[4];
+    for (int i = 0; i < g->n_phases; ++i) {
+        int tw = 1, th = 1, nb = 1;
+        choose_tile(g->phase[i].rows, g->phase[i].cols, tw, th, nb);
+        ptw[i] = tw, pth[i] = th;
+        if (nb < nb_common) nb_common = nb;
+    }
     int tiles = 0;
     for (int i = 0; i < g->n_phases; ++i) {
         PhaseDev& P = p.phase[i];
@@ -391,8 +401,7 @@ extern "C" int rick_conv_tc(void* out, const void* xm, const void* wt, const ric
         if ((Q.rows - 1) * g->out_stride + Q.out_y0 >= g->out_h || (Q.cols - 1) * g->out_stride + Q.out_x0 >= g->out_w ||
             Q.out_y0 < 0 || Q.out_x0 < 0)
             return RICK_ERR_INVALID_ARGUMENT;
-        int tw = 1, th = 1, nb = 1;
-        choose_tile(Q.rows, Q.cols, tw, th, nb);
+        const int tw = ptw[i], th = pth[i], nb = nb_common;
         P.tw = tw, P.th = th, P.nb = nb;
         P.n_mma = ((tw * th * nb + 15) / 16) * 16;
         P.box_bytes = tw * th * nb * kBlockK * 4;
@@ -400,10 +409,12 @@ extern "C" int rick_conv_tc(void* out, const void* xm, const void* wt, const ric
         P.inv_twth = (65536u + tw * th - 1) / (tw * th);
         P.tiles_y = (int)ceil_div(Q.rows, th), P.tiles_x = (int)ceil_div(Q.cols, tw);
         P.tile_begin = tiles;
-        tiles += P.tiles_y * P.tiles_x * (int)ceil_div(g->batch, nb);
+        tiles += P.tiles_y * P.tiles_x;
     }
-    p.pixel_tiles = tiles;
-    p.total_tiles = tiles * p.cout_tiles;
+    p.tiles_per_group = tiles;
+    const long long total = (long long)tiles * ceil_div(g->batch, nb_common) * p.cout_tiles;
+    if (total > 0x7fffffffLL) return RICK_ERR_OVERFLOW;
+    p.total_tiles = (int)total;
     p.out = static_cast<float*>(out);
     if (e) {
         p.out2 = static_cast<float*>(e->out2), p.demod = e->demod, p.noise = e->noise, p.noise_w = e->noise_weight;
