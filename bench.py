@@ -141,7 +141,7 @@ def run_ours(args):
     G, D, Ge, De = build_networks(size, device, seed=1)       # identical weights on every rank (DDP)
     mode = args.mode
     if mode == "auto":
-        mode = "graphs" if world == 1 else "eager"
+        mode = "graphs"
     if mode == "graphs":
         from rick_b200.graphs import GraphedRickAdapter
         adapter = GraphedRickAdapter(cfg, G, D, Ge, De, fused_generator=True)

@@ -12,8 +12,9 @@ buffer written before the replay:
                        reference's concat of repeats (model_probe_tune.py:544-560)
     masks              the byte masks are device resident and updated in place by the Fisher round
 
-The Fisher round itself (once per ``fisher_freq`` iterations) stays eager.  Single-process only: with
-``world_size > 1`` use the eager ``RickAdapter`` (NCCL all-reduce between backward and the optimiser).
+The Fisher round itself (once per ``fisher_freq`` iterations) stays eager.  Under torchrun (world_size > 1) the
+DDP gradient all-reduce is captured inside the graphs (NCCL supports stream capture), so every rank replays the same
+sequence of collectives.
 """
 from __future__ import annotations
 
@@ -31,8 +32,7 @@ from .fused import FusedGenerator
 class GraphedRickAdapter(RickAdapter):
     def __init__(self, cfg: AdaptConfig, generator, discriminator, g_ema, d_ema, fused_generator: bool = True):
         super().__init__(cfg, generator, discriminator, g_ema, d_ema, fused_adam=True, fused_generator=False)
-        if rdist.world_size() > 1:
-            raise RuntimeError("GraphedRickAdapter is single-process; use RickAdapter under torchrun")
+        # world_size > 1: the gradient all-reduce (NCCL) is recorded inside the graphs, between backward and Adam
         if cfg.warmup_iter != 0:
             raise RuntimeError("GraphedRickAdapter captures the post-warm-up iteration (warmup_iter must be 0)")
         g_ratio = cfg.g_reg_every / (cfg.g_reg_every + 1)
@@ -74,6 +74,7 @@ class GraphedRickAdapter(RickAdapter):
         d_loss = d_logistic_loss(real_pred, fake_pred)
         self.d.zero_grad(set_to_none=True)
         d_loss.backward()
+        self._sync_grads(self.d_train)
         self.masks_d.apply(self.d_named, force=True)
         self.d_optim.step()
         return {"d": d_loss.detach(), "real_score": real_pred.mean().detach(), "fake_score": fake_pred.mean().detach()}
@@ -86,6 +87,7 @@ class GraphedRickAdapter(RickAdapter):
         r1_loss = d_r1_loss(real_pred, real_r)
         self.d.zero_grad(set_to_none=True)
         (cfg.r1 / 2 * r1_loss * cfg.d_reg_every + 0 * real_pred[0]).backward()
+        self._sync_grads(self.d_train)
         self.masks_d.apply(self.d_named, force=True)
         self.d_optim.step()
         return {"r1": r1_loss.detach()}
@@ -98,6 +100,7 @@ class GraphedRickAdapter(RickAdapter):
         g_loss = g_nonsaturating_loss(fake_pred)
         self.g.zero_grad(set_to_none=True)
         autograd.backward(g_loss, inputs=self.g_train)
+        self._sync_grads(self.g_train)
         self.masks_g.apply(self.g_named, force=True)
         self.g_optim.step()
         return {"g": g_loss.detach()}
@@ -114,6 +117,7 @@ class GraphedRickAdapter(RickAdapter):
         if cfg.path_batch_shrink:
             weighted = weighted + 0 * fake_img[0, 0, 0, 0]
         autograd.backward(weighted, inputs=self.g_train)
+        self._sync_grads(self.g_train)
         self.masks_g.apply(self.g_named, force=True)
         self.g_optim.step()
         self.mean_path_length.copy_(path_mean)
