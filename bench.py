@@ -260,7 +260,13 @@ def run_ours(args):
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
-        torch.distributed.destroy_process_group()
+        # Tearing down a NCCL process group while CUDA graphs that recorded its collectives are still alive can block
+        # (observed in round 1: the JSON line was out, the process never exited).  Everything is flushed: leave hard.
+        torch.cuda.synchronize()
+        rdist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def _traffic(kernel):
