@@ -239,18 +239,19 @@ __global__ void __launch_bounds__(256) upfirdn2d_tiled(UpfirdnParams p) {
 }
 
 // --------------------------------------------------------------------------------------------------------
-// up = 2 direct kernel (no shared memory)
+// direct kernel (no shared memory) for large maps
 // --------------------------------------------------------------------------------------------------------
-// With up = 2 every output touches only 2 x 2 real samples, so an 8 x 4 output patch needs a 6 x 4 input window: 24
-// scalar loads that neighbouring threads share through L1, then 128 FMAs and eight 128-bit stores.  Dropping the
-// shared-memory staging (loader loop, barrier, LDS) halves the instruction count per output, which is what bounded
-// the tiled kernel at 0.68 of HBM (ncu: 63 % issue active, 48 % ALU, DRAM 53 %).
-template <typename T, int PX, int PY>
-__global__ void __launch_bounds__(256) upfirdn2d_up2_direct(UpfirdnParams p) {
-    constexpr int OX = 4, OY = 8;
-    using WX = Window<2, 1, PX, OX>;
-    using WY = Window<2, 1, PY, OY>;
-    constexpr int WW = WX::size, WH = WY::size;          // 4 x 6 (or 4 x 5) input samples
+// A thread owns an OY x 4 output patch and pulls its input window straight from global memory (neighbouring threads
+// share the samples through L1), then runs the FIR out of registers and leaves 128-bit stores.  Without the
+// shared-memory staging (loader loop, barrier, LDS) the instruction count per output halves and nothing serialises a
+// CTA: up = 2 went from 0.68 to 0.99 of the measured HBM copy bandwidth (round-1 ncu: the tiled kernel was bound by
+// instruction issue / occupancy, 63 % issue active, DRAM 53 %).  CTA = 32 x 8 threads = 128 x (8*OY) outputs.
+template <typename T, int UP, int DOWN, int PX, int PY, int OY>
+__global__ void __launch_bounds__(256) upfirdn2d_direct(UpfirdnParams p) {
+    constexpr int OX = 4;
+    using WX = Window<UP, DOWN, PX, OX>;
+    using WY = Window<UP, DOWN, PY, OY>;
+    constexpr int WW = WX::size, WH = WY::size;
 
     __shared__ float s_taps[16];
     if (threadIdx.x < 16) {
@@ -263,7 +264,6 @@ __global__ void __launch_bounds__(256) upfirdn2d_up2_direct(UpfirdnParams p) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) w[i >> 2][i & 3] = s_taps[i];
 
-    // CTA = 32 x 8 threads = 128 x 64 outputs of one plane
     int b = blockIdx.x;
     const int tile_x = b % p.tiles_x;
     b /= p.tiles_x;
@@ -274,8 +274,8 @@ __global__ void __launch_bounds__(256) upfirdn2d_up2_direct(UpfirdnParams p) {
     if (ox0 >= p.out_w || oy0 >= p.out_h) return;
 
     const T* in = static_cast<const T*>(p.in) + plane * p.in_h * (long long)p.in_w;
-    const int ix0 = ox0 / 2 - p.qx + WX::dmin;
-    const int iy0 = oy0 / 2 - p.qy + WY::dmin;
+    const int ix0 = ox0 * DOWN / UP - p.qx + WX::dmin;
+    const int iy0 = oy0 * DOWN / UP - p.qy + WY::dmin;
     float win[WH][WW];
     bool cok[WW];
 #pragma unroll
@@ -301,14 +301,14 @@ __global__ void __launch_bounds__(256) upfirdn2d_up2_direct(UpfirdnParams p) {
             float a = 0.f;
 #pragma unroll
             for (int ty = 0; ty < 4; ++ty) {
-                const int ny = oy + ty - PY;
-                if (cfloor_mod(ny, 2) != 0) continue;
-                const int dy = cfloor_div(ny, 2) - WY::dmin;
+                const int ny = oy * DOWN + ty - PY;
+                if (cfloor_mod(ny, UP) != 0) continue;
+                const int dy = cfloor_div(ny, UP) - WY::dmin;
 #pragma unroll
                 for (int tx = 0; tx < 4; ++tx) {
-                    const int nx = ox + tx - PX;
-                    if (cfloor_mod(nx, 2) != 0) continue;
-                    const int dx = cfloor_div(nx, 2) - WX::dmin;
+                    const int nx = ox * DOWN + tx - PX;
+                    if (cfloor_mod(nx, UP) != 0) continue;
+                    const int dx = cfloor_div(nx, UP) - WX::dmin;
                     a = fmaf(win[dy][dx], w[ty][tx], a);
                 }
             }
@@ -325,13 +325,13 @@ __global__ void __launch_bounds__(256) upfirdn2d_up2_direct(UpfirdnParams p) {
     }
 }
 
-template <typename T, int PX, int PY>
-static int launch_up2_direct(UpfirdnParams p, cudaStream_t stream) {
+template <typename T, int UP, int DOWN, int PX, int PY, int OY>
+static int launch_direct(UpfirdnParams p, cudaStream_t stream) {
     p.tiles_x = (int)ceil_div(p.out_w, 128);
-    p.tiles_y = (int)ceil_div(p.out_h, 64);
+    p.tiles_y = (int)ceil_div(p.out_h, 8 * OY);
     const long long blocks = (long long)p.tiles_x * p.tiles_y * p.planes;
     if (blocks > 0x7fffffffLL) return RICK_ERR_OVERFLOW;
-    upfirdn2d_up2_direct<T, PX, PY><<<(unsigned)blocks, 256, 0, stream>>>(p);
+    upfirdn2d_direct<T, UP, DOWN, PX, PY, OY><<<(unsigned)blocks, 256, 0, stream>>>(p);
     RICK_CHECK_LAUNCH();
     return RICK_OK;
 }
@@ -398,13 +398,14 @@ static int dispatch(UpfirdnParams p, cudaStream_t stream) {
     p.qx = floor_div(p.pad_x0, up);
     p.qy = floor_div(p.pad_y0, up);
     const int px = floor_mod(p.pad_x0, up), py = floor_mod(p.pad_y0, up);
-    if (up == 1 && p.down_x == 1) return launch_tiled<T, 1, 1, 0, 0, 4>(p, stream);
-    if (up == 1 && p.down_x == 2) return launch_tiled<T, 1, 2, 0, 0, 2>(p, stream);
-    if (p.out_w >= 64 && p.out_h >= 32) {      // large maps: the shared-memory-free kernel; small maps keep the tiled one
-        if (px == 0 && py == 0) return launch_up2_direct<T, 0, 0>(p, stream);
-        if (px == 1 && py == 0) return launch_up2_direct<T, 1, 0>(p, stream);
-        if (px == 0 && py == 1) return launch_up2_direct<T, 0, 1>(p, stream);
-        return launch_up2_direct<T, 1, 1>(p, stream);
+    const bool large = p.out_w >= 64 && p.out_h >= 32;   // large maps: the shared-memory-free kernel
+    if (up == 1 && p.down_x == 1) return large ? launch_direct<T, 1, 1, 0, 0, 4>(p, stream) : launch_tiled<T, 1, 1, 0, 0, 4>(p, stream);
+    if (up == 1 && p.down_x == 2) return large ? launch_direct<T, 1, 2, 0, 0, 4>(p, stream) : launch_tiled<T, 1, 2, 0, 0, 2>(p, stream);
+    if (large) {
+        if (px == 0 && py == 0) return launch_direct<T, 2, 1, 0, 0, 8>(p, stream);
+        if (px == 1 && py == 0) return launch_direct<T, 2, 1, 1, 0, 8>(p, stream);
+        if (px == 0 && py == 1) return launch_direct<T, 2, 1, 0, 1, 8>(p, stream);
+        return launch_direct<T, 2, 1, 1, 1, 8>(p, stream);
     }
     // (an 8-wide patch per thread was measured slower: 3.94 vs 4.43 TB/s -- its two 128-bit stores per row leave every
     //  warp-wide store instruction half-covering its 32-byte sectors; 4-wide keeps each store instruction at 512
