@@ -189,6 +189,29 @@ RICK_API int rick_blur_nhwc(void* out, const void* x, const float* taps, int bat
 RICK_API int rick_to_rgb_nhwc(float* rgb, const float* y, const float* wmod, const float* bias, const float* skip,
                               int batch, int h, int w, int channels, rick_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------- training-time fusions
+ * Channels-last fp32 tensors (batch, hw, channels), channels % 4 == 0.  They replace the broadcast multiplies / adds and
+ * ATen reductions autograd builds around the differentiated ModulatedConv2d (model_probe_tune.py:246-251), NoiseInjection
+ * (:293-298) and FusedLeakyReLU (op/fused_act.py):
+ *   rick_modulate_nhwc             y = x * s[b,c]
+ *   rick_modulate_bwd_nhwc         gx = gy * s[b,c];  gs[b,c] = sum_hw gy * x
+ *   rick_styled_epilogue_nhwc      y = lrelu(a * demod[b,c] + noise_weight * noise[b,hw] + bias[c]) * scale
+ *   rick_styled_epilogue_bwd_nhwc  t = (y > 0 ? gy : gy*alpha) * scale;  ga = t * demod;  gdemod[b,c] = sum_hw t*a;
+ *                                  gbias[c] = sum_{b,hw} t;  gnoise_weight = sum t * noise
+ * workspace: rick_colsum_workspace(batch, hw, channels) bytes.  Reductions are deterministic (fixed-order folds). */
+RICK_API int64_t rick_colsum_workspace(int batch, int64_t hw, int channels);
+RICK_API int rick_modulate_nhwc(void* y, const void* x, const float* s, int batch, int64_t hw, int channels,
+                                rick_stream_t stream);
+RICK_API int rick_modulate_bwd_nhwc(void* gx, float* gs, void* workspace, const void* gy, const void* x, const float* s,
+                                    int batch, int64_t hw, int channels, rick_stream_t stream);
+RICK_API int rick_styled_epilogue_nhwc(void* y, const void* a, const float* demod, const float* noise,
+                                       const float* noise_weight, const float* bias, int batch, int64_t hw,
+                                       int channels, float alpha, float scale, rick_stream_t stream);
+RICK_API int rick_styled_epilogue_bwd_nhwc(void* ga, float* gdemod, float* gbias, float* gnoise_weight, void* workspace,
+                                           const void* gy, const void* y, const void* a, const float* demod,
+                                           const float* noise, int batch, int64_t hw, int channels, float alpha,
+                                           float scale, rick_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------- diagnostics
  * Hardware probe used by scripts/debug_conv_tc.py (not part of the product path): out (128,64) = a (128,32) @
  * b[shift:shift+64] (96,32)^T through one tcgen05.mma whose B descriptor starts `shift` rows into a 128B-swizzled tile. */

@@ -33,6 +33,15 @@ _PROTOTYPES = {
     "rick_bias_act_bwd_nhwc_workspace": (c_int64, [c_int64, c_int64]),
     "rick_bias_act_bwd_nhwc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float,
                                        c_float, c_void_p]),
+    "rick_colsum_workspace": (c_int64, [c_int, c_int64, c_int]),
+    "rick_modulate_nhwc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p]),
+    "rick_modulate_bwd_nhwc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int,
+                                       c_void_p]),
+    "rick_styled_epilogue_nhwc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64,
+                                          c_int, c_float, c_float, c_void_p]),
+    "rick_styled_epilogue_bwd_nhwc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                              c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_float, c_float,
+                                              c_void_p]),
     "rick_fisher_accum": (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int64), c_int, c_int, c_void_p]),
     "rick_fisher_divide": (c_int, [POINTER(c_void_p), POINTER(c_int64), c_int, c_float, c_void_p]),
     "rick_filter_fim": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),

@@ -21,6 +21,8 @@ from typing import Optional
 import torch
 from torch.nn import functional as F
 
+from .op import styled as _styled
+
 _FORCE = os.environ.get("RICK_CONV_BACKEND", "")   # "", "cudnn" or "tc" (tests use it to pin an executor)
 
 
@@ -56,7 +58,8 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
 
 
 def modulated_conv2d(x: torch.Tensor, w: torch.Tensor, s: torch.Tensor, demod: Optional[torch.Tensor],
-                     upsample: bool = False, downsample: bool = False, padding: int = 1, blur=None) -> torch.Tensor:
+                     upsample: bool = False, downsample: bool = False, padding: int = 1, blur=None,
+                     epilogue=None) -> torch.Tensor:
     """out[b] = demod[b] * conv(x[b] * s[b], w)  -- ModulatedConv2d (model_probe_tune.py:243-284) without
     per-sample weights.  ``w`` is the shared (Cout, Cin, k, k) weight already multiplied by the equalised-lr scale,
     ``s`` the (B, Cin) style, ``demod`` the (B, Cout) demodulation or None."""
@@ -72,6 +75,17 @@ def modulated_conv2d(x: torch.Tensor, w: torch.Tensor, s: torch.Tensor, demod: O
         xf = x.permute(0, 2, 3, 1).reshape(b, h * wd, ci)                # free view when x is channels-last
         out = torch.bmm(xf, wmod.transpose(1, 2))                        # (B, HW, 3)
         return out.transpose(1, 2).reshape(b, co, h, wd)
+    if epilogue is not None and demod is not None and not downsample and _styled.fused_ok(x) and w.shape[0] % 4 == 0:
+        # StyledConv: modulate -> conv [-> blur] -> demod + noise + bias + leaky-ReLU, two fused ops around the conv
+        noise, noise_weight, bias, slope, act_scale = epilogue
+        xm = _styled.modulate(x, s)
+        if upsample:
+            out = blur(F.conv_transpose2d(xm, w.transpose(0, 1), stride=2, padding=0))
+        else:
+            out = F.conv2d(xm, w, padding=padding)
+        if noise is None:
+            noise = out.new_empty(out.shape[0], 1, out.shape[2], out.shape[3]).normal_()
+        return _styled.styled_epilogue(out, demod, noise, noise_weight, bias, slope, act_scale)
     xm = x * s[:, :, None, None]
     if upsample:
         out = F.conv_transpose2d(xm, w.transpose(0, 1), stride=2, padding=0)

@@ -201,22 +201,6 @@ __global__ void __launch_bounds__(256) bias_act_bwd_scalar(T* __restrict__ gin, 
     }
 }
 
-// grad_bias[c] = sum_n sum_j src[(n*C + c) * len + j]; one warp per channel, fixed order -> deterministic
-template <typename S>
-__global__ void __launch_bounds__(256) bias_grad_fold(float* __restrict__ grad_bias, const S* __restrict__ src,
-                                                      int n, int c, long long len) {
-    const int lane = threadIdx.x & 31;
-    const int ch = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
-    if (ch >= c) return;
-    float acc = 0.f;
-    for (int b = 0; b < n; ++b) {
-        const S* row = src + ((long long)b * c + ch) * len;
-        for (long long j = lane; j < len; j += 32) acc += Elem<S>::ld(row + j);
-    }
-    acc = warp_sum(acc);
-    if (lane == 0) grad_bias[ch] = acc;
-}
-
 // ---- channels-last: (rows, C) matrix, bias gradient = column sums.  A CTA owns kRowsPerCta rows; thread t owns the
 // float4 column group t % c4 and walks rows t / c4, t / c4 + lanes, ...; row-lane partials are folded through shared
 // memory and written as partial[c][cta] so that bias_grad_fold (fixed order) finishes the reduction.

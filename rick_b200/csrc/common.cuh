@@ -87,4 +87,21 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// grad_bias[c] = sum_n sum_j src[(n*C + c) * len + j]; one warp per channel, fixed order -> deterministic
+template <typename S>
+__global__ void __launch_bounds__(256) bias_grad_fold(float* __restrict__ grad_bias, const S* __restrict__ src,
+                                                      int n, int c, long long len) {
+    const int lane = threadIdx.x & 31;
+    const int ch = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+    if (ch >= c) return;
+    float acc = 0.f;
+    for (int b = 0; b < n; ++b) {
+        const S* row = src + ((long long)b * c + ch) * len;
+        for (long long j = lane; j < len; j += 32) acc += Elem<S>::ld(row + j);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) grad_bias[ch] = acc;
+}
+
+
 }  // namespace rick

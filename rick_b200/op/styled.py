@@ -1,0 +1,122 @@
+"""Fused training-time ops around the differentiated modulated convolution (channels-last fp32):
+
+    modulate(x, s)                                          y = x * s[b, c]
+    styled_epilogue(a, demod, noise, noise_weight, bias)    y = lrelu(a * demod[b,c] + noise_weight * noise + bias[c]) * scale
+
+i.e. ModulatedConv2d's modulation / demodulation in the algebraic form (model_probe_tune.py:246-251), NoiseInjection
+(:293-298) and FusedLeakyReLU (op/fused_act.py) -- each as ONE kernel forward and ONE kernel backward (element-wise part
+plus all broadcast-gradient reductions), instead of the ~10 broadcast / reduce kernels per layer autograd would launch.
+
+Second derivatives (path-length regularisation differentiates through G twice): when ``backward`` runs with grad mode
+enabled (``create_graph=True``) it evaluates the same formulas with differentiable torch ops on the saved tensors, so
+autograd can differentiate them again; the fused kernels serve the ordinary first-order backward.
+"""
+from __future__ import annotations
+
+import torch
+from torch.autograd import Function
+
+from .. import _lib
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def fused_ok(x: torch.Tensor) -> bool:
+    return x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] % 4 == 0 and x.numel() > 0
+
+
+def _cl(x: torch.Tensor) -> torch.Tensor:
+    return x.contiguous(memory_format=torch.channels_last)
+
+
+def _ws(b, hw, c, device):
+    n = max(int(_lib.lib().rick_colsum_workspace(b, hw, c)), 4)
+    return torch.empty(n, dtype=torch.uint8, device=device)
+
+
+class _Modulate(Function):
+    @staticmethod
+    def forward(ctx, x, s):
+        x = _cl(x)
+        s = s.contiguous()
+        b, c, h, w = x.shape
+        y = torch.empty_like(x, memory_format=torch.channels_last)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().rick_modulate_nhwc(y.data_ptr(), x.data_ptr(), s.data_ptr(), b, h * w, c, _stream()),
+                       "rick_modulate_nhwc")
+        ctx.save_for_backward(x, s)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, s = ctx.saved_tensors
+        if torch.is_grad_enabled():                       # double backward requested: differentiable composite
+            return gy * s[:, :, None, None], (gy * x).sum((2, 3))
+        gy = _cl(gy)
+        b, c, h, w = x.shape
+        gx = torch.empty_like(x, memory_format=torch.channels_last)
+        gs = torch.empty(b, c, dtype=torch.float32, device=x.device)
+        ws = _ws(b, h * w, c, x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().rick_modulate_bwd_nhwc(gx.data_ptr(), gs.data_ptr(), ws.data_ptr(), gy.data_ptr(),
+                                                         x.data_ptr(), s.data_ptr(), b, h * w, c, _stream()),
+                       "rick_modulate_bwd_nhwc")
+        return gx, gs
+
+
+class _StyledEpilogue(Function):
+    @staticmethod
+    def forward(ctx, a, demod, noise, noise_weight, bias, alpha, scale):
+        a = _cl(a)
+        demod = demod.contiguous()
+        b, c, h, w = a.shape
+        noise = noise.expand(b, 1, h, w).reshape(b, h * w).contiguous()
+        y = torch.empty_like(a, memory_format=torch.channels_last)
+        with torch.cuda.device(a.device):
+            _lib.check(_lib.lib().rick_styled_epilogue_nhwc(y.data_ptr(), a.data_ptr(), demod.data_ptr(), noise.data_ptr(),
+                                                            noise_weight.data_ptr(), bias.data_ptr(), b, h * w, c,
+                                                            float(alpha), float(scale), _stream()),
+                       "rick_styled_epilogue_nhwc")
+        ctx.save_for_backward(a, demod, noise, noise_weight, y)
+        ctx.alpha, ctx.scale = alpha, scale
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        a, demod, noise, noise_weight, y = ctx.saved_tensors
+        b, c, h, w = a.shape
+        if torch.is_grad_enabled():                       # double backward requested: differentiable composite
+            t = torch.where(y > 0, gy, gy * ctx.alpha) * ctx.scale
+            nz = noise.view(b, 1, h, w)
+            return (t * demod[:, :, None, None], (t * a).sum((2, 3)), None, (t * nz).sum().reshape(1), t.sum((0, 2, 3)),
+                    None, None)
+        gy = _cl(gy)
+        ga = torch.empty_like(a, memory_format=torch.channels_last)
+        gd = torch.empty(b, c, dtype=torch.float32, device=a.device)
+        gb = torch.empty(c, dtype=torch.float32, device=a.device)
+        gnw = torch.empty(1, dtype=torch.float32, device=a.device)
+        ws = _ws(b, h * w, c, a.device)
+        with torch.cuda.device(a.device):
+            _lib.check(_lib.lib().rick_styled_epilogue_bwd_nhwc(ga.data_ptr(), gd.data_ptr(), gb.data_ptr(), gnw.data_ptr(),
+                                                                ws.data_ptr(), gy.data_ptr(), y.data_ptr(), a.data_ptr(),
+                                                                demod.data_ptr(), noise.data_ptr(), b, h * w, c,
+                                                                float(ctx.alpha), float(ctx.scale), _stream()),
+                       "rick_styled_epilogue_bwd_nhwc")
+        return ga, gd, None, gnw, gb, None, None
+
+
+def modulate(x: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
+    """x * s[:, :, None, None] (channels-last result)."""
+    if fused_ok(x):
+        return _Modulate.apply(x, s)
+    return x * s[:, :, None, None]
+
+
+def styled_epilogue(a, demod, noise, noise_weight, bias, negative_slope=0.2, scale=2 ** 0.5):
+    """lrelu(a * demod[b,c] + noise_weight * noise + bias[c]) * scale; ``noise`` is (B or 1, 1, H, W)."""
+    if fused_ok(a):
+        return _StyledEpilogue.apply(a, demod, noise, noise_weight, bias, negative_slope, scale)
+    from .fused_act import fused_leaky_relu
+    return fused_leaky_relu(a * demod[:, :, None, None] + noise_weight * noise, bias, negative_slope, scale)

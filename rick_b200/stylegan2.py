@@ -36,6 +36,14 @@ from .op import FusedLeakyReLU, fused_leaky_relu, upfirdn2d
 _CHANNELS_LAST = os.environ.get("RICK_CHANNELS_LAST", "1") != "0"
 
 
+_FUSED_STYLED = os.environ.get("RICK_FUSED_STYLED", "1") != "0"   # fused modulate / demod-noise-bias-act ops in StyledConv
+
+
+def set_fused_styled(flag: bool) -> None:
+    global _FUSED_STYLED
+    _FUSED_STYLED = bool(flag)
+
+
 def set_channels_last(flag: bool) -> None:
     global _CHANNELS_LAST
     _CHANNELS_LAST = bool(flag)
@@ -177,7 +185,9 @@ class ModulatedConv2d(nn.Module):
         return (f"{self.__class__.__name__}({self.in_channel}, {self.out_channel}, {self.kernel_size}, "
                 f"upsample={self.upsample}, downsample={self.downsample})")
 
-    def forward(self, input, style):
+    def forward(self, input, style, epilogue=None):
+        """``epilogue`` = (noise, noise_weight, bias, slope, scale): StyledConv hands its NoiseInjection + FusedLeakyReLU
+        down so that demodulation, noise, bias and activation run as one fused op behind the convolution."""
         s = self.modulation(style)                                   # (B, Cin)
         w = self.weight[0] * self.scale                              # (Cout, Cin, k, k), shared by the batch
         demod = None
@@ -185,7 +195,7 @@ class ModulatedConv2d(nn.Module):
             wsq = w.pow(2).sum([2, 3])                               # (Cout, Cin)
             demod = torch.rsqrt(F.linear(s.pow(2), wsq) + self.eps)  # (B, Cout)
         return _conv.modulated_conv2d(input, w, s, demod, upsample=self.upsample, downsample=self.downsample,
-                                      padding=self.padding, blur=getattr(self, "blur", None))
+                                      padding=self.padding, blur=getattr(self, "blur", None), epilogue=epilogue)
 
 
 class NoiseInjection(nn.Module):
@@ -219,6 +229,9 @@ class StyledConv(nn.Module):
         self.activate = FusedLeakyReLU(out_channel)
 
     def forward(self, input, style, noise=None):
+        if _FUSED_STYLED and _conv._styled.fused_ok(input) and self.conv.demodulate and self.conv.out_channel % 4 == 0:
+            return self.conv(input, style, epilogue=(noise, self.noise.weight, self.activate.bias,
+                                                     self.activate.negative_slope, self.activate.scale))
         out = self.conv(input, style)
         out = self.noise(out, noise=noise)
         return self.activate(out)

@@ -244,3 +244,51 @@ def test_fused_leaky_relu_channels_last(shape, op):
     _close(ggx, wgx)
     _close(ggb, wgb, 1e-4)
     _close(ggg, wgg, 1e-4)
+
+
+@pytest.mark.parametrize("shape", [(2, 512, 4, 4), (2, 128, 37, 29), (3, 12, 9, 9), (2, 256, 64, 64)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_fused_modulate_and_styled_epilogue(shape):
+    """rick_modulate_* / rick_styled_epilogue_* (fwd, fused bwd with all broadcast-gradient reductions, and the
+    differentiable double-backward branch) against the plain torch composite on the CPU in float64."""
+    from rick_b200.op import styled
+    b, c, h, w = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x, s = torch.randn(b, c, h, w, generator=g), torch.randn(b, c, generator=g)
+    d = torch.rand(b, c, generator=g) + 0.5
+    noise, nw, bias = torch.randn(b, 1, h, w, generator=g), torch.randn(1, generator=g), torch.randn(c, generator=g)
+    go = torch.randn(b, c, h, w, generator=g)
+
+    def composite(x, s, d, noise, nw, bias):
+        a = x * s[:, :, None, None]
+        return torch.nn.functional.leaky_relu(a * d[:, :, None, None] + nw * noise + bias[None, :, None, None], 0.2) * 2 ** 0.5
+
+    def fused(x, s, d, noise, nw, bias):
+        return styled.styled_epilogue(styled.modulate(x, s), d, noise, nw, bias)
+
+    def run(fn, dev, dt):
+        leaves = [t.to(dev, dt).requires_grad_(True) for t in (x, s, d, nw, bias)]
+        xi, si, di, nwi, bi = leaves
+        y = fn(xi, si, di, noise.to(dev, dt), nwi, bi)
+        gi = go.to(dev, dt).requires_grad_(True)
+        grads = torch.autograd.grad(y, leaves, gi, create_graph=True)
+        # second order: differentiate a scalar of the first-order grads w.r.t. x, s and the upstream gradient
+        scal = sum((gr * gr).sum() for gr in grads)
+        gg = torch.autograd.grad(scal, [xi, si, gi], allow_unused=True)
+        return y.detach(), [gr.detach() for gr in grads], gg
+
+    wy, wg, wgg = run(composite, "cpu", torch.float64)
+    gy, gg_, ggg = run(fused, "cuda", torch.float32)
+    _close(gy, wy)
+    for a_, b_ in zip(gg_, wg):
+        _close(a_, b_, 2e-4)
+    for a_, b_ in zip(ggg, wgg):
+        assert (a_ is None) == (b_ is None)
+        if a_ is not None:
+            _close(a_, b_, 2e-3)
+    # first-order fused kernels (no create_graph): same numbers as the composite branch
+    leaves = [t.cuda().requires_grad_(True) for t in (x, s, d, nw, bias)]
+    y = fused(leaves[0], leaves[1], leaves[2], noise.cuda(), leaves[3], leaves[4])
+    grads = torch.autograd.grad(y, leaves, go.cuda())
+    for a_, b_ in zip(grads, wg):
+        _close(a_, b_, 2e-4)
