@@ -39,8 +39,8 @@ def _ws(b, hw, c, device):
 class _Modulate(Function):
     @staticmethod
     def forward(ctx, x, s):
-        x = _cl(x)
-        s = s.contiguous()
+        # x is channels-last and s contiguous (the wrapper converts OUTSIDE the Function, differentiably): the saved
+        # tensors must be the inputs themselves or the double-backward branch would treat them as constants
         b, c, h, w = x.shape
         y = torch.empty_like(x, memory_format=torch.channels_last)
         with torch.cuda.device(x.device):
@@ -69,10 +69,8 @@ class _Modulate(Function):
 class _StyledEpilogue(Function):
     @staticmethod
     def forward(ctx, a, demod, noise, noise_weight, bias, alpha, scale):
-        a = _cl(a)
-        demod = demod.contiguous()
+        # a channels-last, demod / noise (B, HW) / bias contiguous: converted by the wrapper (see _Modulate.forward)
         b, c, h, w = a.shape
-        noise = noise.expand(b, 1, h, w).reshape(b, h * w).contiguous()
         y = torch.empty_like(a, memory_format=torch.channels_last)
         with torch.cuda.device(a.device):
             _lib.check(_lib.lib().rick_styled_epilogue_nhwc(y.data_ptr(), a.data_ptr(), demod.data_ptr(), noise.data_ptr(),
@@ -110,13 +108,16 @@ class _StyledEpilogue(Function):
 def modulate(x: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
     """x * s[:, :, None, None] (channels-last result)."""
     if fused_ok(x):
-        return _Modulate.apply(x, s)
+        return _Modulate.apply(_cl(x), s.contiguous())
     return x * s[:, :, None, None]
 
 
 def styled_epilogue(a, demod, noise, noise_weight, bias, negative_slope=0.2, scale=2 ** 0.5):
     """lrelu(a * demod[b,c] + noise_weight * noise + bias[c]) * scale; ``noise`` is (B or 1, 1, H, W)."""
     if fused_ok(a):
-        return _StyledEpilogue.apply(a, demod, noise, noise_weight, bias, negative_slope, scale)
+        b, c, h, w = a.shape
+        noise = noise.detach().expand(b, 1, h, w).reshape(b, h * w).contiguous()      # noise is data, not a parameter
+        return _StyledEpilogue.apply(_cl(a), demod.contiguous(), noise, noise_weight, bias.contiguous(), negative_slope,
+                                     scale)
     from .fused_act import fused_leaky_relu
     return fused_leaky_relu(a * demod[:, :, None, None] + noise_weight * noise, bias, negative_slope, scale)
