@@ -183,8 +183,11 @@ class FilterMasks:
         for name, st in self.state.items():
             p = named_params[name]
             g = p.grad
-            if g is not None and not g.is_contiguous():
-                raise RuntimeError(f"FilterMasks.apply: gradient of {name} is not contiguous")
+            for t in (p, g):
+                # rows (= filters, dim 0) must be the outermost, dense blocks of memory: true for contiguous and for
+                # channels-last 4-D tensors alike
+                if t is not None and not (t.is_contiguous() or t.is_contiguous(memory_format=torch.channels_last)):
+                    raise RuntimeError(f"FilterMasks.apply: {name} (or its gradient) is not stored filter-major")
             r = st.numel()
             params.append(p.data_ptr())
             grads.append(g.data_ptr() if g is not None else None)

@@ -189,11 +189,14 @@ class ModulatedConv2d(nn.Module):
         """``epilogue`` = (noise, noise_weight, bias, slope, scale): StyledConv hands its NoiseInjection + FusedLeakyReLU
         down so that demodulation, noise, bias and activation run as one fused op behind the convolution."""
         s = self.modulation(style)                                   # (B, Cin)
-        w = self.weight[0] * self.scale                              # (Cout, Cin, k, k), shared by the batch
+        # conv(x * s, scale * W) == conv(x * (scale * s), W): the equalised-lr scale rides on the (B, Cin) style, so
+        # the 2.4 M-float weight is not rescaled (one multiply kernel + one in backward per layer and call)
+        w = self.weight[0]                                           # (Cout, Cin, k, k), shared by the batch
         demod = None
         if self.demodulate:
             wsq = w.pow(2).sum([2, 3])                               # (Cout, Cin)
-            demod = torch.rsqrt(F.linear(s.pow(2), wsq) + self.eps)  # (B, Cout)
+            demod = torch.rsqrt(F.linear(s.pow(2), wsq) * (self.scale ** 2) + self.eps)   # (B, Cout)
+        s = s * self.scale
         return _conv.modulated_conv2d(input, w, s, demod, upsample=self.upsample, downsample=self.downsample,
                                       padding=self.padding, blur=getattr(self, "blur", None), epilogue=epilogue)
 
@@ -397,6 +400,10 @@ class Discriminator(nn.Module):
         self.final_conv = ConvLayer(in_channel + 1, channels[4], 3)
         self.final_linear = nn.Sequential(EqualLinear(channels[4] * 4 * 4, channels[4], activation="fused_lrelu"),
                                           EqualLinear(channels[4], 1))
+        if _CHANNELS_LAST:
+            # keep the 4-D conv weights in channels-last memory (same shapes / state_dict): the library convolutions then
+            # take weight * scale as is instead of re-laying it out on every call (~190 copy kernels per iteration)
+            self.to(memory_format=torch.channels_last)
 
     def estimate_fisher(self, loglikelihood):
         return _estimate_fisher(self, loglikelihood)
