@@ -22,9 +22,9 @@ bench)
   timeout 600 python -u bench.py --steps ${BENCH_STEPS:-20} --warmup 3 ${BENCH_ARGS} > gpurun_out/bench${BENCH_TAG}.json 2> gpurun_out/bench${BENCH_TAG}.err
   echo "bench rc=$?"; tail -c 4500 gpurun_out/bench${BENCH_TAG}.json; tail -5 gpurun_out/bench${BENCH_TAG}.err ;;
 ncu)
-  timeout 420 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 12000 --csv \
+  timeout 560 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 2600 --csv \
       --log-file gpurun_out/launches${NCU_TAG}.csv \
-      python -u bench.py --steps 2 --warmup 3 --no-cpu-baseline --quick --cuda-profiler ${NCU_BENCH_ARGS:---mode eager} \
+      python -u bench.py --steps 1 --warmup 3 --no-cpu-baseline --quick --cuda-profiler ${NCU_BENCH_ARGS:---mode eager} \
       > gpurun_out/ncu_bench${NCU_TAG}.log 2>&1
   echo "ncu launches rc=$?"
   timeout 300 ncu --set full --clock-control none --import-source on \

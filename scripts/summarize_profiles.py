@@ -46,8 +46,10 @@ def launches(tag, fname="launches.csv"):
     ours = sum(v for k, v in rows if any(o in k for o in OURS))
     with open(os.path.join(PROF, f"{tag}_launches.md"), "w") as f:
         f.write(f"# {tag}: ncu launch list (gpu__time_duration.sum, --clock-control none)\n\n")
-        f.write(f"command: `python bench.py --steps 2 --warmup 3 --no-cpu-baseline` (first {len(rows)} launches; cold-cache, "
-                f"serialised -- compare SHARES, not absolutes)\n\n")
+        f.write(f"command: `ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none "
+                f"python bench.py --steps 1 --warmup 3 --quick --cuda-profiler --mode eager` -- the timed iteration of the "
+                f"bench workload, launched eagerly (the default graphs mode replays the same kernels); {len(rows)} launches; "
+                f"cold-cache, serialised -- compare SHARES, not absolutes\n\n")
         f.write(f"total {tot / 1e3:.2f} ms over {len(rows)} launches; rick_b200 kernels {ours / 1e3:.2f} ms "
                 f"({100 * ours / max(tot, 1e-9):.1f} %)\n\n| kernel | launches | total us | share % | avg us |\n|---|---:|---:|---:|---:|\n")
         for k, (n, v) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
