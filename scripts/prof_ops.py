@@ -16,7 +16,7 @@ wt = torch.randn(9, 512, 512, device=dev) / 68.0
 geom = ct.geom_conv(64, 64, 64, 512, 512, 3, 1, 1)
 geomT = ct.geom_conv_transpose_s2(64, 32, 32, 512, 512)
 xt = torch.randn(64, 32, 32, 512, device=dev)
-for _ in range(2):
+for _ in range(2):   # pass 0 warms up (8 matching kernel launches, skipped by ncu -s 8), pass 1 is captured
     y = op.upfirdn2d(x, taps4, up=2, pad=(2, 1))          # (32,512,256,256)
     z = op.upfirdn2d(x, taps1, pad=(2, 2))                # D blur, NCHW
     d = op.upfirdn2d(x, taps1, down=2, pad=(1, 1))
