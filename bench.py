@@ -421,11 +421,12 @@ def _oracle_adapter(threads):
     from oracle import synth
     from rick_b200.adapt import AdaptConfig, DrawStream
     torch.set_num_threads(threads)
-    cfg = AdaptConfig(size=256, batch=2, warmup_iter=0, fisher_freq=50, num_fisher_img=5, fisher_quantile=40.0,
+    size = int(os.environ.get("RICK_BENCH_REF_SIZE", "256"))     # tests shrink the CPU arm; the bench always runs 256
+    cfg = AdaptConfig(size=size, batch=2, warmup_iter=0, fisher_freq=50, num_fisher_img=5, fisher_quantile=40.0,
                       prune_quantile=0.1)
-    gp, dp = synth.g_state(256, 1), synth.d_state(256, 2)
+    gp, dp = synth.g_state(size, 1), synth.d_state(size, 2)
     A = ao.OracleAdapter(cfg, gp, dp, {k: v.clone() for k, v in gp.items()}, {k: v.clone() for k, v in dp.items()})
-    return A, DrawStream(5, "cpu"), synth.shots(10, 256, 0)
+    return A, DrawStream(5, "cpu"), synth.shots(10, size, 0)
 
 
 def cpu_baseline(max_seconds=40.0):
