@@ -147,7 +147,8 @@ class RickAdapter:
         self.fg = None
         if fused_generator:
             from .fused import FusedGenerator
-            self.fg = FusedGenerator(generator)
+            if FusedGenerator.supports(generator):          # e.g. not the 64 / 32-channel layers of 512 / 1024 px
+                self.fg = FusedGenerator(generator)
 
     # ------------------------------------------------------------------------------------------ Fisher round
     def fisher_round(self, latents: torch.Tensor, reals: torch.Tensor, layer_noise: Optional[list] = None):
@@ -305,7 +306,8 @@ def generate_samples(generator, n_samples: int, batch: int, latent: int = 512, r
     gen = torch.Generator(device=device)
     if fused:                                   # tcgen05 executor (rick_b200.fused), same images up to TF32 rounding
         from .fused import FusedGenerator
-        generator = FusedGenerator(generator)
+        if FusedGenerator.supports(generator):
+            generator = FusedGenerator(generator)
     for k in range(rank, n_batches, world):
         gen.manual_seed(seed + k)
         z = torch.randn(batch, latent, generator=gen, device=device)

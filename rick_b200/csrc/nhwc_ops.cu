@@ -54,16 +54,24 @@ __global__ void __launch_bounds__(128, 3) blur_nhwc_kernel(BlurParams p) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) w[i >> 2][i & 3] = s_taps[i];
 
-    const long long total = (long long)p.batch * p.strips_y * p.strips_x * p.c4;
+    // Work item = (sample, row strip, column strip, group of 32 channel-float4s).  The 4 warps of a CTA take 4 ADJACENT
+    // column strips of the same channel group, so the 3 input columns neighbouring strips share are served by L1 (with
+    // channel-major numbering they sat in different CTAs: 4 % L1 hit rate, 2.5x L2 traffic in the first profile).
+    const int cgb_n = (p.c4 + 31) / 32;                       // 32-lane channel groups
+    const int sxb_n = (p.strips_x + 3) / 4;                   // blocks of 4 column strips
+    const long long total = (long long)p.batch * p.strips_y * sxb_n * cgb_n;
     const float nw = p.noise ? __ldg(p.noise_w) : 0.f;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int cg = (int)(idx % p.c4);
-        long long r = idx / p.c4;
-        const int sx = (int)(r % p.strips_x);
-        r /= p.strips_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (long long item = blockIdx.x; item < total; item += gridDim.x) {
+        const int cgb = (int)(item % cgb_n);
+        long long r = item / cgb_n;
+        const int sxb = (int)(r % sxb_n);
+        r /= sxb_n;
         const int sy = (int)(r % p.strips_y);
         const int b = (int)(r / p.strips_y);
+        const int cg = cgb * 32 + lane;
+        const int sx = sxb * 4 + warp;
+        if (cg >= p.c4 || sx >= p.strips_x) continue;
         const int ox0 = sx * TX, oy0 = sy * TY;
         const int ix0 = ox0 - p.pad0, iy0 = oy0 - p.pad0;
         const float4* xin = reinterpret_cast<const float4*>(p.x) + (long long)b * p.in_h * p.in_w * p.c4 + cg;
@@ -186,8 +194,7 @@ extern "C" int rick_blur_nhwc(void* out, const void* x, const float* taps, int b
     const long long threads16 = (long long)batch * ceil_div(p.out_h, 16) * p.strips_x * p.c4;
     const int ty = threads16 >= (long long)kNumSMs * 3 * 128 * 8 ? 16 : 4;
     p.strips_y = (int)ceil_div(p.out_h, ty);
-    const long long total = (long long)batch * p.strips_y * p.strips_x * p.c4;
-    long long blocks = ceil_div(total, 128);
+    long long blocks = (long long)batch * p.strips_y * ceil_div(p.strips_x, 4) * ceil_div(p.c4, 32);   // one item per CTA pass
     const long long cap = (long long)kNumSMs * 48;
     if (blocks > cap) blocks = cap;
     if (ty == 16) blur_nhwc_kernel<16><<<(unsigned)blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);

@@ -59,6 +59,14 @@ class FusedGenerator:
         self.g = generator
         self.refresh()
 
+    @staticmethod
+    def supports(generator) -> bool:
+        """True when every StyledConv of ``generator`` fits the tcgen05 kernel (Cin % 32 == 0, Cout % 128 == 0): all
+        layers up to 256 px at channel_multiplier 2.  The 512 / 1024 px layers (64 / 32 channels) do not; callers then
+        keep the module path."""
+        convs = [generator.conv1] + list(generator.convs)
+        return all(ct.supported(c.conv.in_channel, c.conv.out_channel) for c in convs)
+
     def refresh(self):
         """Re-pack weights after the parameters changed (optimiser step / EMA update)."""
         g = self.g

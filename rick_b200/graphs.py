@@ -42,7 +42,7 @@ class GraphedRickAdapter(RickAdapter):
         self.d_optim = optim.Adam(self.d_train, lr=cfg.lr * d_ratio, betas=(0 ** d_ratio, 0.99 ** d_ratio), fused=True,
                                   capturable=True)
         dev = self.device
-        self.fg = FusedGenerator(generator) if fused_generator else None
+        self.fg = FusedGenerator(generator) if (fused_generator and FusedGenerator.supports(generator)) else None
         self._real = torch.zeros(cfg.batch, 3, cfg.size, cfg.size, device=dev)
         self._inject = {k: torch.full((), generator.n_latent, dtype=torch.long, device=dev) for k in ("d", "g", "path")}
         self._layer = torch.arange(generator.n_latent, device=dev).view(1, -1, 1)
