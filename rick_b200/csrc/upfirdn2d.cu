@@ -19,7 +19,11 @@
 //   upfirdn2d_generic any taps / factors / minor: one thread per output sample, gathers valid taps from global
 //                     memory (L1/L2 provide the reuse).  Correctness path for the shapes the model never issues
 //                     (e.g. the 12x12 taps of non_leaking.py).
+#include <algorithm>
+#include <type_traits>
+
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace rick {
 
@@ -36,6 +40,9 @@ struct UpfirdnParams {
     int log_txn, log_tyn, tpn;   // thread grid inside a CTA: txn x tyn threads per plane, tpn planes
     int itw, ith, itw_pad;       // staged input tile (per plane) and its row pitch in floats
     int tiles_x, tiles_y;
+    // rows kernel only
+    int tr, sr, ncg, nseg, edge;   // output rows per CTA / per warp item, 32-column groups, row segments, edge columns
+    long long total;               // elements in the whole input tensor
 };
 
 // --------------------------------------------------------------------------------------------------------
@@ -325,6 +332,231 @@ __global__ void __launch_bounds__(256) upfirdn2d_direct(UpfirdnParams p) {
     }
 }
 
+// --------------------------------------------------------------------------------------------------------
+// rows kernel: up = 1 (blur / decimating blur) on large planes, staged through shared memory by one bulk copy
+// --------------------------------------------------------------------------------------------------------
+// For up = 1 every output needs a 4x4 window of distinct inputs, so the direct kernel spends most of its time on
+// strided, mis-aligned window loads (odd widths 2^k + 1 are the common case: the blur after a transposed conv reads
+// 129 -> 128, D's blur writes 128 -> 129).  Here a CTA owns TR full-width output rows of one plane: the input rows
+// they need are ONE contiguous span of the NCHW tensor, fetched with a single cp.async.bulk (aligned down/up to
+// 16 B; rows outside the image are simply not fetched and read as zero).  Several CTAs are resident per SM, so
+// their bulk copies overlap the FIR of the others without holding registers.  Compute: lane = output column, a warp
+// slides down SR rows keeping the 4x4 window in registers (4 conflict-free LDS + 16 FMA per output for down = 1), and
+// every warp-wide store is 128 contiguous bytes.  The <= 4 columns left over when out_w = 32 k + r are done
+// transposed (lane = row), so 129-wide planes do not pay for a fifth, almost empty column group.
+template <typename T> __device__ __forceinline__ float smem_val(const T* p);
+template <> __device__ __forceinline__ float smem_val<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float smem_val<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+// Shared-memory image of a tile: element (row y, col x) of the plane sits at index  so + (y - y_lo) * in_w + x, for the
+// R = TR*DOWN + 4 - DOWN rows starting at y_lo = oy0*DOWN - pad_y0, x in [-3, in_w + 3).  Rows outside the image are
+// zero-filled by the CTA, so the FIR loop reads them like any other row.  Columns outside the image read whatever
+// neighbours them in the span (finite data or zeroed slack) and are cancelled by a per-thread 0/1 mask folded into
+// the taps once -- the inner loop carries no predicates.  (|pad_x| <= 3 guarantees every window keeps one real column.)
+template <typename T, int DOWN>
+__global__ void __launch_bounds__(256, 4) upfirdn2d_rows(UpfirdnParams p) {
+    constexpr int A = 16 / (int)sizeof(T);   // elements per 16 bytes
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    __shared__ uint64_t s_bar;
+    __shared__ float s_taps[16];
+    T* s_in = reinterpret_cast<T*>(s_raw);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int tile_y = blockIdx.y;
+    const long long plane = blockIdx.x;
+    const int oy0 = tile_y * p.tr;
+    const int oy1 = min(oy0 + p.tr, p.out_h);
+    const int in_w = p.in_w;
+    const int R = p.tr * DOWN + 4 - DOWN;
+    const int y_lo = oy0 * DOWN - p.pad_y0;
+    // rows [r0, r1) of the image intersect the tile's rows [y_lo, y_lo + R)
+    const int r0 = max(y_lo, 0);
+    const int r1 = min(y_lo + R, p.in_h);
+    const T* in = static_cast<const T*>(p.in);
+
+    int so = 3, d0 = 0, d1 = 0;          // origin offset; [d0, d1) = smem elements written by the bulk copy
+    long long a0 = 0, a1 = 0, e1 = 0;
+    if (r1 > r0) {
+        const long long e0 = (plane * p.in_h + r0) * (long long)in_w;
+        e1 = e0 + (long long)(r1 - r0) * in_w;
+        a0 = e0 & ~(long long)(A - 1);
+        a1 = (e1 + A - 1) & ~(long long)(A - 1);
+        const long long cap = p.total & ~(long long)(A - 1);
+        if (a1 > cap) a1 = cap;                      // never read past the tensor: the < 16 B tail goes by hand
+        if (a1 < a0) a1 = a0;
+        const int shift = (int)(e0 - a0);
+        const int rel = (r0 - y_lo) * in_w;
+        so = ((shift - rel) % A + A) % A;            // makes the bulk destination 16-byte aligned
+        if (so < 3) so += A;
+        d0 = so + rel - shift;
+        d1 = d0 + (int)(a1 - a0);
+    }
+    const int nb = so + R * in_w + A;                // buffer length in elements
+    const int row0_idx = so + (r0 - y_lo) * in_w, rowend_idx = so + (r1 - y_lo) * in_w;   // fetched rows' extent
+    // zero everything the bulk copy does not write (padding rows, slack)
+    for (int i = tid; i < d0; i += blockDim.x) s_in[i] = T(0.f);
+    for (int i = d1 + tid; i < nb; i += blockDim.x) s_in[i] = T(0.f);
+    if (tid < 16) {
+        const int ty = tid >> 2, tx = tid & 3;
+        const int ky = p.flip ? ty : 3 - ty, kx = p.flip ? tx : 3 - tx;
+        s_taps[tid] = __ldg(p.taps + ky * 4 + kx);
+    }
+    if (tid == 0) {
+        tc::mbar_init(&s_bar, 1);
+        tc::fence_mbar_init();
+    }
+    __syncthreads();
+    if (r1 > r0 && a1 < e1 && tid < (int)(e1 - a1)) s_in[d1 + tid] = in[a1 + tid];   // tail the copy may not touch
+    const uint32_t bytes = (uint32_t)(d1 - d0) * (uint32_t)sizeof(T);
+    if (bytes && tid == 0) {
+        tc::mbar_arrive_expect_tx(&s_bar, bytes);
+        tc::bulk_load_1d(s_in + d0, in + a0, bytes, &s_bar);
+    }
+    // One warp polls the mbarrier (a polling warp burns issue slots the resident CTAs' FIR loops need); the rest
+    // park on the hardware barrier.  The aligned copy also brought a few elements of the rows before r0 / after
+    // r1 - 1: where those rows are padding they must read as zero -- warp 0 repairs them before releasing the CTA.
+    if (warp == 0) {
+        if (bytes) tc::mbar_wait(&s_bar, 0);
+        const bool fix_top = r1 > r0 && r0 > y_lo;
+        const bool fix_bot = r1 > r0 && r1 < y_lo + R;
+        if (fix_top && lane < row0_idx - d0) s_in[d0 + lane] = T(0.f);
+        if (fix_bot && lane < d1 - rowend_idx) s_in[rowend_idx + lane] = T(0.f);
+    }
+    __syncthreads();
+
+    T* outp = static_cast<T*>(p.out) + plane * p.out_h * (long long)p.out_w;
+
+    // ---- main items: (32-column group, row segment); lane = output column ----
+    for (int item = warp; item < p.ncg * p.nseg; item += nwarps) {
+        const int cg = item % p.ncg, seg = item / p.ncg;
+        const int ox = cg * 32 + lane;
+        const int oys = oy0 + seg * p.sr;
+        const int n = min(oys + p.sr, oy1) - oys;
+        if (n <= 0) continue;
+        const int x0 = ox * DOWN - p.pad_x0;
+        const bool active = ox < p.out_w;
+        // taps with the column mask folded in, paired along x for the packed fp32 FMA (FFMA2: two lanes per issue slot)
+        float2 wm[4][2];
+#pragma unroll
+        for (int tx = 0; tx < 4; ++tx) {
+            const float m = (active && x0 + tx >= 0 && x0 + tx < in_w) ? 1.f : 0.f;
+#pragma unroll
+            for (int ty = 0; ty < 4; ++ty) {
+                if (tx & 1) wm[ty][tx >> 1].y = s_taps[ty * 4 + tx] * m;
+                else wm[ty][tx >> 1].x = s_taps[ty * 4 + tx] * m;
+            }
+        }
+        // inactive lanes (beyond out_w) stay inside the buffer by reading column 0
+        const T* sp = s_in + so + (oys * DOWN - p.pad_y0 - y_lo) * in_w + (active ? x0 : 0);
+        float2 win[4][2];
+        auto load_row = [&](const T* q, float2 (&v)[2]) {
+            v[0].x = smem_val<T>(q), v[0].y = smem_val<T>(q + 1), v[1].x = smem_val<T>(q + 2), v[1].y = smem_val<T>(q + 3);
+        };
+#pragma unroll
+        for (int r = 0; r < 4 - DOWN; ++r) load_row(sp + r * in_w, win[r]);
+        sp += (4 - DOWN) * in_w;
+        T* orow = outp + (long long)oys * p.out_w + ox;
+        auto step = [&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+#pragma unroll
+            for (int d = 0; d < DOWN; ++d) load_row(sp + d * in_w, win[(j * DOWN + (4 - DOWN) + d) & 3]);
+            sp += DOWN * in_w;
+            float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int ty = 0; ty < 4; ++ty) {
+                a0 = __ffma2_rn(win[(j * DOWN + ty) & 3][0], wm[ty][0], a0);
+                a1 = __ffma2_rn(win[(j * DOWN + ty) & 3][1], wm[ty][1], a1);
+            }
+            if (active) Elem<T>::st(orow, (a0.x + a0.y) + (a1.x + a1.y));
+            orow += p.out_w;
+        };
+        int i = 0;
+        for (; i + 4 <= n; i += 4) {
+            step(std::integral_constant<int, 0>{});
+            step(std::integral_constant<int, 1>{});
+            step(std::integral_constant<int, 2>{});
+            step(std::integral_constant<int, 3>{});
+        }
+        if (i < n) step(std::integral_constant<int, 0>{});
+        if (i + 1 < n) step(std::integral_constant<int, 1>{});
+        if (i + 2 < n) step(std::integral_constant<int, 2>{});
+    }
+
+    // ---- edge columns (out_w % 32 <= 4) ----
+    // One column of TR outputs reads a 4-column strip of the tile; with a row pitch that is a multiple of 32 words
+    // (in_w = 128, 256) a lane-per-row mapping puts all 32 lanes on one bank.  Instead every warp takes 8 output
+    // rows of the column: lane = (row r = lane >> 2, tap column tx = lane & 3) loads the strip once (8-way conflict,
+    // the minimum for 4 banks), rows are exchanged with shuffles and the 4 tap columns reduced with two more.
+    {
+        constexpr int SPAN = 8 * DOWN + 4 - DOWN;      // input rows behind 8 output rows
+        constexpr int NV = (SPAN + 7) / 8;
+        const int r = lane >> 2, tx = lane & 3;
+        for (int item = warp; item < p.edge * (p.tr >> 3); item += nwarps) {
+            const int ox = p.out_w - p.edge + item % p.edge;
+            const int oyb = oy0 + (item / p.edge) * 8;
+            if (oyb >= oy1) continue;
+            const int x = ox * DOWN - p.pad_x0 + tx;
+            const bool xok = x >= 0 && x < in_w;
+            const T* sp = s_in + so + (oyb * DOWN - p.pad_y0 - y_lo) * in_w + (xok ? x : 0);
+            float v[NV];
+#pragma unroll
+            for (int k = 0; k < NV; ++k) v[k] = (xok && r + 8 * k < SPAN) ? smem_val<T>(sp + (r + 8 * k) * in_w) : 0.f;
+            float a = 0.f;
+#pragma unroll
+            for (int ty = 0; ty < 4; ++ty) {
+                const int yr = r * DOWN + ty;             // input row (relative) feeding output row r through tap row ty
+                const int src = ((yr & 7) << 2) | tx;
+                float got = 0.f;
+#pragma unroll
+                for (int k = 0; k < NV; ++k) {
+                    const float t = __shfl_sync(0xffffffffu, v[k], src);
+                    if ((yr >> 3) == k) got = t;
+                }
+                a = fmaf(got, s_taps[ty * 4 + tx], a);
+            }
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            if (tx == 0 && oyb + r < oy1) Elem<T>::st(outp + (long long)(oyb + r) * p.out_w + ox, a);
+        }
+    }
+}
+
+// returns RICK_OK after launching, or -1 when the shape does not fit this kernel (caller falls back)
+template <typename T, int DOWN>
+static int launch_rows(UpfirdnParams p, cudaStream_t stream) {
+    constexpr int A = 16 / (int)sizeof(T);
+    if (!aligned_to(p.in, 16)) return -1;
+    // every window must keep at least one real column (see the kernel header)
+    const int pad_x1 = (p.out_w - 1) * DOWN + 4 - p.pad_x0 - p.in_w;   // right padding actually consumed
+    if (p.pad_x0 > 3 || pad_x1 > 3) return -1;
+    // rows per CTA: as many as ~40 KB of staging holds (fewer, longer CTAs amortise the per-CTA and per-item set-up,
+    // which is what bounds this kernel: it is instruction-issue limited, not bandwidth limited)
+    int tr = 64;
+    auto smem_for = [&](int t) { return ((size_t)(t * DOWN + 4 - DOWN) * p.in_w + 2 * A + 3) * sizeof(T); };
+    while (tr > 8 && smem_for(tr) > 40 * 1024) tr >>= 1;
+    if (smem_for(tr) > 44 * 1024) return -1;
+    // balance the row tiles (129 rows -> 48 + 48 + 33, not 64 + 64 + 1); tr stays a multiple of 16
+    const int ntile = (int)ceil_div(p.out_h, tr);
+    tr = (int)ceil_div(ceil_div(p.out_h, ntile), 16) * 16;
+    p.tr = tr;
+    p.edge = (p.out_w % 32 <= 4) ? p.out_w % 32 : 0;
+    p.ncg = p.out_w / 32 + ((p.out_w % 32 > 4) ? 1 : 0);
+    if (p.ncg < 1) return -1;
+    // one item per warp, >= 4 warps: the per-CTA and per-item set-up is replicated per warp, so fewer, longer warps win
+    int nseg = 1;
+    while (p.ncg * nseg < 4 && tr / (nseg * 2) >= 8 && tr % (nseg * 8) == 0) nseg <<= 1;
+    p.nseg = nseg;
+    const int nthreads = 32 * std::min(8, std::max(4, p.ncg * nseg));
+    p.sr = tr / nseg;
+    p.tiles_y = (int)ceil_div(p.out_h, tr);
+    p.total = p.planes * p.in_h * (long long)p.in_w;
+    if (p.planes > 0x7fffffffLL || p.tiles_y > 65535) return -1;
+    const size_t smem = (smem_for(tr) + 15) & ~(size_t)15;
+    upfirdn2d_rows<T, DOWN><<<dim3((unsigned)p.planes, (unsigned)p.tiles_y), nthreads, smem, stream>>>(p);
+    RICK_CHECK_LAUNCH();
+    return RICK_OK;
+}
+
 template <typename T, int UP, int DOWN, int PX, int PY, int OY>
 static int launch_direct(UpfirdnParams p, cudaStream_t stream) {
     p.tiles_x = (int)ceil_div(p.out_w, 128);
@@ -399,6 +631,10 @@ static int dispatch(UpfirdnParams p, cudaStream_t stream) {
     p.qy = floor_div(p.pad_y0, up);
     const int px = floor_mod(p.pad_x0, up), py = floor_mod(p.pad_y0, up);
     const bool large = p.out_w >= 64 && p.out_h >= 32;   // large maps: the shared-memory-free kernel
+    if (up == 1 && large) {                               // blur / decimating blur: bulk-staged full-width row tiles
+        const int rc = p.down_x == 1 ? launch_rows<T, 1>(p, stream) : launch_rows<T, 2>(p, stream);
+        if (rc >= 0) return rc;
+    }
     if (up == 1 && p.down_x == 1) return large ? launch_direct<T, 1, 1, 0, 0, 4>(p, stream) : launch_tiled<T, 1, 1, 0, 0, 4>(p, stream);
     if (up == 1 && p.down_x == 2) return large ? launch_direct<T, 1, 2, 0, 0, 4>(p, stream) : launch_tiled<T, 1, 2, 0, 0, 2>(p, stream);
     if (large) {

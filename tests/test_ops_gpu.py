@@ -67,6 +67,36 @@ def test_upfirdn2d_model_shapes_fwd_bwd(shape, op):
     _close(gg, gw)
 
 
+ROWS_SHAPES = [
+    # (N, C, H, W, down, pad) large up=1 planes -> the bulk-staged rows kernel: odd widths, left-over column counts of
+    # 0 / 1 / 4 (edge columns) / 6 / 31 (partial group), ragged last row tile, crops, 1024-px-D widths, down = 2
+    (2, 3, 129, 129, 1, (1, 1)), (2, 3, 128, 128, 1, (2, 2)), (1, 2, 71, 73, 1, (1, 1)), (1, 2, 140, 101, 1, (2, 2)),
+    (1, 2, 90, 98, 1, (-1, -2)), (1, 1, 513, 513, 1, (1, 1)), (1, 1, 40, 1025, 1, (2, 2)), (2, 3, 128, 128, 2, (1, 1)),
+    (1, 2, 257, 259, 2, (2, 2)), (1, 2, 150, 131, 2, (0, 3)), (3, 1, 67, 200, 1, (3, 0)),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("shape", ROWS_SHAPES, ids=[f"{s[0]}x{s[1]}x{s[2]}x{s[3]}_d{s[4]}p{s[5][0]}{s[5][1]}" for s in ROWS_SHAPES])
+def test_upfirdn2d_rows_kernel_asymmetric_taps(shape, dtype, op):
+    """Random (asymmetric) 4x4 taps so a transposed / flipped window cannot pass; forward and backward (flipped taps)."""
+    n, c, h, w, down, pad = shape
+    g = torch.Generator().manual_seed(h * 977 + w * 13 + down)
+    x = torch.randn(n, c, h, w, generator=g).to(dtype)
+    taps = torch.randn(4, 4, generator=g)
+    xo = x.float().clone().requires_grad_(True)
+    want = ops.upfirdn2d(xo, taps, 1, down, pad)
+    xg = x.cuda().requires_grad_(True)
+    got = op.upfirdn2d(xg, taps.cuda(), 1, down, pad)
+    assert got.dtype == dtype and tuple(got.shape) == tuple(want.shape)
+    rel = REL if dtype == torch.float32 else 1e-2
+    _close(got.float(), want.detach(), rel)
+    go = torch.randn(want.shape, generator=g).to(dtype)
+    (gw,) = torch.autograd.grad(want, xo, go.float())
+    (gg,) = torch.autograd.grad(got, xg, go.cuda())
+    _close(gg.float(), gw, rel)
+
+
 def test_upfirdn2d_double_backward(op):
     g = torch.Generator().manual_seed(5)
     x = torch.randn(2, 3, 12, 12, generator=g)
