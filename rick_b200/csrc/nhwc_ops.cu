@@ -11,6 +11,7 @@
 // Both are HBM-bound streaming kernels.  Threads of a warp cover 32 consecutive float4 channel groups of one pixel,
 // so every load / store instruction moves 512 contiguous bytes.
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace rick {
 namespace {
@@ -133,6 +134,163 @@ __global__ void __launch_bounds__(128, 3) blur_nhwc_kernel(BlurParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// streaming variant for large maps: TMA-staged rows, partial sums in registers, packed fp32 FMAs
+// ---------------------------------------------------------------------------------------------------------------
+// The register-ring kernel above tops out near half the HBM rate on the 64..256-px layers: ~64 scalar FMAs per
+// float4 output already fill the issue slots a memory-bound kernel can spare, and 162 registers leave 12 warps per SM
+// to cover DRAM latency.  This version changes both:
+//   * A CTA owns (sample, 32 channels, 32 output columns, a segment of output rows) and streams the input rows it
+//     needs through a 4-stage ring of TMA boxes (32 ch x 35 columns x 4 rows, 17.5 KB each).  The tensor map zero-fills
+//     everything outside the image, so padding costs no predicate; the copies run ahead of the math without holding
+//     registers, which is what hides the DRAM latency.  Halo re-reads: 3 of 35 columns, 3 rows per segment.
+//   * Nothing but the current input row is kept: each row is scattered into the 4 output rows it touches (partial
+//     sums for 2 columns x 4 pending rows), and a row is stored when its fourth input row has passed.
+//   * The FMAs are issued as FFMA2 (two channels per instruction): 32 instead of 64 per float4 output.
+// Thread = (column pair, float4 channel group): 16 x 8 = 128 threads; every LDS.128 of a warp reads four full 128-byte
+// pixel rows (no bank conflicts), every STG.128 writes four.
+constexpr int SB_TW = 32, SB_RS = 4, SB_NS = 4, SB_CB = 32, SB_BOXW = SB_TW + 3;
+constexpr int SB_STAGE_BYTES = SB_BOXW * SB_RS * SB_CB * 4;
+
+__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
+template <bool EPI>   // EPI: the StyledConv epilogue (demod / noise / bias / activation / next-layer modulation) is applied
+__global__ void __launch_bounds__(128, 3)
+blur_nhwc_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ BlurParams p, int seg_rows) {
+    extern __shared__ unsigned char sb_raw[];
+    __shared__ uint64_t s_full[SB_NS];
+    __shared__ float s_taps[16];
+    unsigned char* stages = sb_raw + ((128u - (tc::smem_u32(sb_raw) & 127u)) & 127u);   // 128-byte aligned TMA destinations
+
+    const int tid = threadIdx.x, quad = tid & 7, cp = tid >> 3;
+    const int sx = blockIdx.x % p.strips_x, cgi = blockIdx.x / p.strips_x;
+    const int b = blockIdx.z;
+    const int oy0 = blockIdx.y * seg_rows;
+    const int rows_here = min(seg_rows, p.out_h - oy0);
+    const int n_stage = (rows_here + 3 + SB_RS - 1) / SB_RS;
+    const int x_in0 = sx * SB_TW - p.pad0, y_in0 = oy0 - p.pad0, c0 = cgi * SB_CB;
+
+    if (tid < 16) {
+        const int ty = tid >> 2, tx = tid & 3;
+        s_taps[tid] = p.flip ? __ldg(p.taps + ty * 4 + tx) : __ldg(p.taps + (3 - ty) * 4 + (3 - tx));
+    }
+    if (tid == 0) {
+        tc::tma_prefetch_desc(&tmap);
+#pragma unroll
+        for (int s = 0; s < SB_NS; ++s) tc::mbar_init(&s_full[s], 1);
+        tc::fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int s = 0; s < SB_NS && s < n_stage; ++s) {
+            tc::mbar_arrive_expect_tx(&s_full[s], SB_STAGE_BYTES);
+            tc::tma_load_4d(stages + s * SB_STAGE_BYTES, &tmap, &s_full[s], c0, x_in0, y_in0 + s * SB_RS, b);
+        }
+    }
+    float2 w2[4][4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w2[i >> 2][i & 3] = make_float2(s_taps[i], s_taps[i]);
+
+    const int cg = cgi * (SB_CB / 4) + quad;                 // float4 channel group of this thread
+    const int ox0 = sx * SB_TW + 2 * cp;
+    const bool ok0 = ox0 < p.out_w, ok1 = ox0 + 1 < p.out_w;
+    // running pointers to this thread's two output pixels of the next completed row (column 1 = one pixel further)
+    const long long pix0 = ((long long)b * p.out_h + oy0) * p.out_w + ox0;
+    float4* o1 = reinterpret_cast<float4*>(p.out) + pix0 * p.c4 + cg;
+    float4* o2 = EPI && p.out2 ? reinterpret_cast<float4*>(p.out2) + pix0 * p.c4 + cg : nullptr;
+    const float* nzp = EPI && p.noise ? p.noise + pix0 : nullptr;
+    const long long row_f4 = (long long)p.out_w * p.c4;
+
+    float2 dm[2], bs[2], sn[2];
+    dm[0] = dm[1] = sn[0] = sn[1] = make_float2(1.f, 1.f);
+    bs[0] = bs[1] = make_float2(0.f, 0.f);
+    float nw = 0.f;
+    if (EPI) {
+        if (p.demod) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p.demod) + (long long)b * p.c4 + cg);
+            dm[0] = make_float2(t.x, t.y), dm[1] = make_float2(t.z, t.w);
+        }
+        if (p.bias) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias) + cg);
+            bs[0] = make_float2(t.x, t.y), bs[1] = make_float2(t.z, t.w);
+        }
+        if (p.s_next) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p.s_next) + (long long)b * p.c4 + cg);
+            sn[0] = make_float2(t.x, t.y), sn[1] = make_float2(t.z, t.w);
+        }
+        if (p.noise) nw = __ldg(p.noise_w);
+    }
+
+    float2 acc[2][4][2];                                     // [column][pending output row slot][channel pair]
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i >> 3][(i >> 1) & 3][i & 1] = make_float2(0.f, 0.f);
+
+    auto finish = [&](int col, float2 lo, float2 hi) {       // epilogue + store of one float4 output
+        if (!EPI) {
+            st_stream_f4(o1 + (long long)col * p.c4, make_float4(lo.x, lo.y, hi.x, hi.y));
+            return;
+        }
+        const float nz = nzp ? nw * __ldg(nzp + col) : 0.f;
+        const float2 nz2 = make_float2(nz, nz);
+        float2 v[2] = {__fadd2_rn(__ffma2_rn(lo, dm[0], nz2), bs[0]), __fadd2_rn(__ffma2_rn(hi, dm[1], nz2), bs[1])};
+        if (p.act) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float2 neg = __fmul2_rn(v[h], make_float2(p.alpha, p.alpha));
+                v[h] = __fmul2_rn(make_float2(v[h].x > 0.f ? v[h].x : neg.x, v[h].y > 0.f ? v[h].y : neg.y),
+                                  make_float2(p.scale, p.scale));
+            }
+        }
+        const float2 m0 = __fmul2_rn(v[0], sn[0]), m1 = __fmul2_rn(v[1], sn[1]);
+        if (o2) {
+            st_stream_f4(o1 + (long long)col * p.c4, make_float4(v[0].x, v[0].y, v[1].x, v[1].y));
+            st_stream_f4(o2 + (long long)col * p.c4, make_float4(m0.x, m0.y, m1.x, m1.y));
+        } else {
+            st_stream_f4(o1 + (long long)col * p.c4, make_float4(m0.x, m0.y, m1.x, m1.y));   // sn == 1 unless only the modulated copy is wanted
+        }
+    };
+
+    for (int st = 0; st < n_stage; ++st) {
+        const int slot = st & (SB_NS - 1);
+        tc::mbar_wait(&s_full[slot], (st / SB_NS) & 1);
+        const float4* sbase = reinterpret_cast<const float4*>(stages + slot * SB_STAGE_BYTES) + (2 * cp) * (SB_CB / 4) + quad;
+#pragma unroll
+        for (int j = 0; j < SB_RS; ++j) {
+            float4 v[5];
+#pragma unroll
+            for (int t = 0; t < 5; ++t) v[t] = sbase[(j * SB_BOXW + t) * (SB_CB / 4)];
+#pragma unroll
+            for (int col = 0; col < 2; ++col)
+#pragma unroll
+                for (int ty = 0; ty < 4; ++ty) {
+                    const int s = (j - ty) & 3;              // input row 4*st + j is tap row ty of output row 4*st + j - ty
+#pragma unroll
+                    for (int tx = 0; tx < 4; ++tx) {
+                        acc[col][s][0] = f2_fma(make_float2(v[col + tx].x, v[col + tx].y), w2[ty][tx], acc[col][s][0]);
+                        acc[col][s][1] = f2_fma(make_float2(v[col + tx].z, v[col + tx].w), w2[ty][tx], acc[col][s][1]);
+                    }
+                }
+            const int done = (j + 1) & 3;                    // the slot that just received its tap row 3
+            const int o = st * SB_RS + j - 3;
+            if (o >= 0 && o < rows_here) {
+                if (ok0) finish(0, acc[0][done][0], acc[0][done][1]);
+                if (ok1) finish(1, acc[1][done][0], acc[1][done][1]);
+                o1 += row_f4;
+                if (EPI) {
+                    if (o2) o2 += row_f4;
+                    if (nzp) nzp += p.out_w;
+                }
+            }
+            acc[0][done][0] = acc[0][done][1] = acc[1][done][0] = acc[1][done][1] = make_float2(0.f, 0.f);
+        }
+        __syncthreads();                                     // every thread is done reading this slot
+        if (tid == 0 && st + SB_NS < n_stage) {
+            tc::mbar_arrive_expect_tx(&s_full[slot], SB_STAGE_BYTES);
+            tc::tma_load_4d(stages + slot * SB_STAGE_BYTES, &tmap, &s_full[slot], c0, x_in0, y_in0 + (st + SB_NS) * SB_RS, b);
+        }
+    }
+}
+
 // one warp per pixel: 3 dot products over C channels, warp-shuffle reduction
 __global__ void __launch_bounds__(256) to_rgb_nhwc_kernel(float* __restrict__ rgb, const float* __restrict__ y,
                                                           const float* __restrict__ wmod,
@@ -188,6 +346,47 @@ extern "C" int rick_blur_nhwc(void* out, const void* x, const float* taps, int b
         if ((p.demod && !aligned_to(p.demod, 16)) || (p.bias && !aligned_to(p.bias, 16)) ||
             (p.s_next && !aligned_to(p.s_next, 16)) || (p.out2 && !aligned_to(p.out2, 16)))
             return RICK_ERR_ALIGNMENT;
+    }
+    // ---- large maps: the TMA-streamed kernel ----
+    if (p.out_w >= 48 && p.out_h >= 16 && channels % SB_CB == 0 && batch <= 65535) {
+        EncodeTiledFn encode = get_encode_tiled();
+        if (!encode) return RICK_ERR_UNSUPPORTED;
+        CUtensorMap tmap;
+        cuuint64_t dims[4] = {(cuuint64_t)channels, (cuuint64_t)in_w, (cuuint64_t)in_h, (cuuint64_t)batch};
+        cuuint64_t strides[3] = {(cuuint64_t)channels * 4, (cuuint64_t)channels * in_w * 4,
+                                 (cuuint64_t)channels * in_w * in_h * 4};
+        cuuint32_t box[4] = {SB_CB, SB_BOXW, SB_RS, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        if (encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(x), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return RICK_ERR_INVALID_ARGUMENT;
+        p.strips_x = (int)ceil_div(p.out_w, SB_TW);
+        const int ncg = channels / SB_CB;
+        // output rows per CTA: 4k + 1 so that rows + 3 fills whole 4-row stages; shorter segments when CTAs are scarce
+        int seg = 61;
+        for (int cand : {61, 33, 17}) {
+            seg = cand;
+            if ((long long)p.strips_x * ncg * ceil_div(p.out_h, cand) * batch >= (long long)kNumSMs * 6) break;
+        }
+        const int nseg = (int)ceil_div(p.out_h, seg);
+        if ((long long)p.strips_x * ncg > 0x7fffffffLL || nseg > 65535) return RICK_ERR_OVERFLOW;
+        const size_t smem = (size_t)SB_NS * SB_STAGE_BYTES + 128;
+        const bool epi = p.demod || p.noise || p.bias || p.s_next || p.out2 || p.act;
+        auto kernel = epi ? blur_nhwc_stream_kernel<true> : blur_nhwc_stream_kernel<false>;
+        {   // once per device and variant; kept out of later calls so that launches can be recorded into CUDA graphs
+            static bool attr_done[64][2] = {};
+            int dev = 0;
+            RICK_CUDA_TRY(cudaGetDevice(&dev));
+            if (dev < 0 || dev >= 64 || !attr_done[dev][epi]) {
+                RICK_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                if (dev >= 0 && dev < 64) attr_done[dev][epi] = true;
+            }
+        }
+        kernel<<<dim3((unsigned)(p.strips_x * ncg), (unsigned)nseg, (unsigned)batch), 128, smem,
+                 static_cast<cudaStream_t>(stream)>>>(tmap, p, seg);
+        RICK_CHECK_LAUNCH();
+        return RICK_OK;
     }
     // long row marches amortise the 3-row halo but serialise; use them only when there are >= 8 waves of CTAs anyway
     p.strips_x = (int)ceil_div(p.out_w, TX);
