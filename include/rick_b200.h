@@ -19,6 +19,7 @@
  *   rick_percentile           train:285-286, 298-299, 352-353 (np.percentile, 'linear')
  *   rick_decide               train:312-314, 324-330, 368-384 (np.where index sets) + 386-393 (cumulative prune union)
  *   rick_mask_apply           train:427-437, 482-492, 521-539, 566-585 (index_put on param / grad per filter)
+ *   rick_adam_mask_ema        the same masks + torch.optim.Adam.step (train:916-925) + accumulate() (train:68-73, 697-698)
  *   rick_modconv_*            gan_training/models/model_probe_tune.py:243-284 (ModulatedConv2d: modulate, demodulate,
  *                             grouped conv / transposed conv) -- tcgen05 implicit GEMM, see rick_b200/csrc/conv_tc.cu
  */
@@ -128,6 +129,26 @@ RICK_API int rick_decide(uint8_t* state, uint8_t* zero_mask, const float* fim, i
 RICK_API int rick_mask_apply(float* const* param, float* const* grad, const uint8_t* const* state,
                     const uint8_t* const* zero, const int64_t* rows, const int64_t* inner, int count,
                     rick_stream_t stream);
+
+/* Fused multi-tensor optimiser step: filter masks + Adam + EMA in one pass, one launch per network.  Replaces, per
+ * optimiser step of the reference loop, the index_put mask application (train:427-437, 482-492, 521-539, 566-585),
+ * torch.optim.Adam.step (betas (0, 0.99**ratio), train:916-925) and, when ema[t] is given, accumulate() (train:68-73,
+ * 697-698).  HOST tables of length count; entry t describes rows[t] x inner[t] contiguous float32 elements:
+ *   param[t]                 updated in place
+ *   grad[t]                  NULL = no optimiser update for this tensor (EMA / pruning only); never written
+ *   exp_avg[t], exp_avg_sq[t] Adam moments (required when grad[t] is given)
+ *   ema[t]                   NULL = no EMA; else ema = ema * ema_decay + (1 - ema_decay) * param (after the update)
+ *   state[t], zero[t]        per-row bytes as for rick_mask_apply (NULL = unmasked): rows with (state & 1) or zero take
+ *                            a zero gradient, rows with zero have param set to 0
+ *   step[t]                  DEVICE pointer to this tensor's float step count t >= 1, already incremented by the caller
+ *                            (torch.optim.Adam keeps one count per parameter: a tensor that starts receiving
+ *                            gradients late starts its bias correction late; device-resident so that the launch can
+ *                            be recorded into a CUDA graph).  Required when grad[t] is given. */
+RICK_API int rick_adam_mask_ema(float* const* param, const float* const* grad, float* const* exp_avg,
+                       float* const* exp_avg_sq, float* const* ema, const uint8_t* const* state,
+                       const uint8_t* const* zero, const float* const* step, const int64_t* rows, const int64_t* inner,
+                       int count, float lr, float beta1, float beta2, float eps, float ema_decay,
+                       rick_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------- tcgen05 convolution
  * Implicit-GEMM convolution on NHWC fp32 activations (TF32 tensor-core math, fp32 accumulate), replacing the grouped

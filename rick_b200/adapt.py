@@ -120,9 +120,11 @@ class RickAdapter:
     """Owns the four networks, the two Adam optimisers, the Fisher accumulators and the filter masks."""
 
     def __init__(self, cfg: AdaptConfig, generator, discriminator, g_ema, d_ema, fused_adam: bool = True,
-                 fused_generator: bool = False):
+                 fused_generator: bool = False, fused_optim: Optional[bool] = None):
         """``fused_generator``: produce the D step's fake batch (a no-grad generator call) with the tcgen05 executor
-        (rick_b200.fused.FusedGenerator) instead of the differentiable module path."""
+        (rick_b200.fused.FusedGenerator) instead of the differentiable module path.
+        ``fused_optim``: one rick_adam_mask_ema launch per optimiser step (masks + Adam + EMA, rick_b200.optim) instead
+        of rick_mask_apply + torch.optim.Adam + the foreach EMA (default: on for CUDA parameters)."""
         self.cfg = cfg
         self.g, self.d, self.g_ema, self.d_ema = generator, discriminator, g_ema, d_ema
         self.device = next(generator.parameters()).device
@@ -134,15 +136,25 @@ class RickAdapter:
         self.g_train = [p for n, p in self.g_named.items() if "convs" in n]
         self.d_train = [p for n, p in self.d_named.items()
                         if ("convs" in n and "convs.0" not in n) or "final" in n]
-        kw = dict(fused=True) if fused_adam and self.device.type == "cuda" else {}
-        self.g_optim = optim.Adam(self.g_train, lr=cfg.lr * g_ratio, betas=(0 ** g_ratio, 0.99 ** g_ratio), **kw)
-        self.d_optim = optim.Adam(self.d_train, lr=cfg.lr * d_ratio, betas=(0 ** d_ratio, 0.99 ** d_ratio), **kw)
         self.acc_g = rick.FisherAccumulator(g_ema.named_parameters())
         self.acc_d = rick.FisherAccumulator(d_ema.named_parameters())
         self.masks_g = rick.FilterMasks(rick.generator_layers(dict(g_ema.named_parameters())), self.device)
         self.masks_d = rick.FilterMasks(rick.discriminator_layers(dict(d_ema.named_parameters())), self.device)
         self.mean_path_length = torch.zeros((), device=self.device)
         self.ema_decay = 0.5 ** (32 / (10 * 1000))
+        self.fused_optim = (self.device.type == "cuda") if fused_optim is None else bool(fused_optim)
+        g_hyper = dict(lr=cfg.lr * g_ratio, betas=(0 ** g_ratio, 0.99 ** g_ratio))
+        d_hyper = dict(lr=cfg.lr * d_ratio, betas=(0 ** d_ratio, 0.99 ** d_ratio))
+        if self.fused_optim:
+            from .optim import FusedMaskedAdam
+            self.g_optim = FusedMaskedAdam(self.g_named, self.g_train, masks=self.masks_g, ema_decay=self.ema_decay,
+                                           ema_named=dict(g_ema.named_parameters()), **g_hyper)
+            self.d_optim = FusedMaskedAdam(self.d_named, self.d_train, masks=self.masks_d, ema_decay=self.ema_decay,
+                                           ema_named=dict(d_ema.named_parameters()), **d_hyper)
+        else:
+            kw = dict(fused=True) if fused_adam and self.device.type == "cuda" else {}
+            self.g_optim = optim.Adam(self.g_train, **g_hyper, **kw)
+            self.d_optim = optim.Adam(self.d_train, **d_hyper, **kw)
         self._ema_pairs = None
         self.fg = None
         if fused_generator:
@@ -220,12 +232,14 @@ class RickAdapter:
         self.d.zero_grad(set_to_none=True)
         d_loss.backward()
         self._sync_grads(self.d_train)
-        if after_warmup:
-            self.masks_d.apply(self.d_named)
-        self.d_optim.step()
+        r1_iter = i % cfg.d_reg_every == 0
+        path_iter = i % cfg.g_reg_every == 0 and after_warmup
+        # with the fused optimiser the EMA rides on the LAST update of each network in this iteration (the weights do
+        # not move again before train:697-698 would read them)
+        self._optim_step("d", after_warmup, ema=not r1_iter)
 
         # ---- R1 (train:462-493) ----
-        if i % cfg.d_reg_every == 0:
+        if r1_iter:
             real_r = real_img.detach().requires_grad_(True)
             real_pred, _ = self.d(real_r)
             real_pred = real_pred.view(real_r.size(0), -1).mean(dim=1).unsqueeze(1)
@@ -233,9 +247,7 @@ class RickAdapter:
             self.d.zero_grad(set_to_none=True)
             (cfg.r1 / 2 * r1_loss * cfg.d_reg_every + 0 * real_pred[0]).backward()
             self._sync_grads(self.d_train)
-            if after_warmup:
-                self.masks_d.apply(self.d_named)
-            self.d_optim.step()
+            self._optim_step("d", after_warmup, ema=True)
             out["r1"] = r1_loss.detach()
 
         # ---- G step (train:500-540) ----
@@ -248,8 +260,7 @@ class RickAdapter:
             self.g.zero_grad(set_to_none=True)
             autograd.backward(g_loss, inputs=self.g_train)
             self._sync_grads(self.g_train)
-            self.masks_g.apply(self.g_named)
-            self.g_optim.step()
+            self._optim_step("g", True, ema=not path_iter)
         else:
             with torch.no_grad():                       # warm-up: the loss is only logged (train:518-519)
                 fake_img, _ = self.g(z, inject_index=inject, noise=noise_of(cfg.batch))
@@ -257,7 +268,7 @@ class RickAdapter:
         out["g"] = g_loss.detach()
 
         # ---- path-length regularisation (train:546-589) ----
-        if i % cfg.g_reg_every == 0 and after_warmup:
+        if path_iter:
             pb = max(1, cfg.batch // cfg.path_batch_shrink)
             z = draws.mixing_latents(pb, cfg.latent, cfg.mixing)
             inject = draws.randint(1, self.g.n_latent - 1) if len(z) == 2 else None
@@ -270,13 +281,26 @@ class RickAdapter:
                 weighted = weighted + 0 * fake_img[0, 0, 0, 0]
             autograd.backward(weighted, inputs=self.g_train)
             self._sync_grads(self.g_train)
-            self.masks_g.apply(self.g_named)
-            self.g_optim.step()
+            self._optim_step("g", True, ema=True)
             out["path"], out["path_length"] = path_loss.detach(), path_lengths.mean().detach()
 
         # ---- EMA (train:697-698) ----
-        self._ema()
+        if not self.fused_optim:
+            self._ema()
+        elif not after_warmup:
+            self.g_optim.ema_only()                     # G took no optimiser step during warm-up
         return out
+
+    def _optim_step(self, net: str, masked: bool, ema: bool = False, force_masks: bool = False):
+        """Masks + optimiser step of network ``net`` ("g" / "d"); with the fused optimiser also its EMA when ``ema``."""
+        opt = self.g_optim if net == "g" else self.d_optim
+        if self.fused_optim:
+            opt.step(apply_masks=masked, ema=ema)
+            return
+        if masked:
+            (self.masks_g if net == "g" else self.masks_d).apply(self.g_named if net == "g" else self.d_named,
+                                                                 force=force_masks)
+        opt.step()
 
     @staticmethod
     def _sync_grads(params):

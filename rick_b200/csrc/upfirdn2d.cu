@@ -535,9 +535,9 @@ static int launch_rows(UpfirdnParams p, cudaStream_t stream) {
     auto smem_for = [&](int t) { return ((size_t)(t * DOWN + 4 - DOWN) * p.in_w + 2 * A + 3) * sizeof(T); };
     while (tr > 8 && smem_for(tr) > 40 * 1024) tr >>= 1;
     if (smem_for(tr) > 44 * 1024) return -1;
-    // balance the row tiles (129 rows -> 48 + 48 + 33, not 64 + 64 + 1); tr stays a multiple of 16
+    // balance the row tiles (129 rows -> 48 + 48 + 33, not 64 + 64 + 1); tr stays a multiple of 8 and never grows
     const int ntile = (int)ceil_div(p.out_h, tr);
-    tr = (int)ceil_div(ceil_div(p.out_h, ntile), 16) * 16;
+    tr = std::min(tr, (int)ceil_div(ceil_div(p.out_h, ntile), 8) * 8);
     p.tr = tr;
     p.edge = (p.out_w % 32 <= 4) ? p.out_w % 32 : 0;
     p.ncg = p.out_w / 32 + ((p.out_w % 32 > 4) ? 1 : 0);

@@ -30,17 +30,20 @@ from .fused import FusedGenerator
 
 
 class GraphedRickAdapter(RickAdapter):
-    def __init__(self, cfg: AdaptConfig, generator, discriminator, g_ema, d_ema, fused_generator: bool = True):
-        super().__init__(cfg, generator, discriminator, g_ema, d_ema, fused_adam=True, fused_generator=False)
+    def __init__(self, cfg: AdaptConfig, generator, discriminator, g_ema, d_ema, fused_generator: bool = True,
+                 fused_optim: bool = True):
+        super().__init__(cfg, generator, discriminator, g_ema, d_ema, fused_adam=True, fused_generator=False,
+                         fused_optim=fused_optim)
         # world_size > 1: the gradient all-reduce (NCCL) is recorded inside the graphs, between backward and Adam
         if cfg.warmup_iter != 0:
             raise RuntimeError("GraphedRickAdapter captures the post-warm-up iteration (warmup_iter must be 0)")
         g_ratio = cfg.g_reg_every / (cfg.g_reg_every + 1)
         d_ratio = cfg.d_reg_every / (cfg.d_reg_every + 1)
-        self.g_optim = optim.Adam(self.g_train, lr=cfg.lr * g_ratio, betas=(0 ** g_ratio, 0.99 ** g_ratio), fused=True,
-                                  capturable=True)
-        self.d_optim = optim.Adam(self.d_train, lr=cfg.lr * d_ratio, betas=(0 ** d_ratio, 0.99 ** d_ratio), fused=True,
-                                  capturable=True)
+        if not self.fused_optim:                        # (the fused optimiser keeps its step count on the device already)
+            self.g_optim = optim.Adam(self.g_train, lr=cfg.lr * g_ratio, betas=(0 ** g_ratio, 0.99 ** g_ratio),
+                                      fused=True, capturable=True)
+            self.d_optim = optim.Adam(self.d_train, lr=cfg.lr * d_ratio, betas=(0 ** d_ratio, 0.99 ** d_ratio),
+                                      fused=True, capturable=True)
         dev = self.device
         self.fg = FusedGenerator(generator) if (fused_generator and FusedGenerator.supports(generator)) else None
         self._real = torch.zeros(cfg.batch, 3, cfg.size, cfg.size, device=dev)
@@ -75,8 +78,7 @@ class GraphedRickAdapter(RickAdapter):
         self.d.zero_grad(set_to_none=True)
         d_loss.backward()
         self._sync_grads(self.d_train)
-        self.masks_d.apply(self.d_named, force=True)
-        self.d_optim.step()
+        self._optim_step("d", True, force_masks=True)
         return {"d": d_loss.detach(), "real_score": real_pred.mean().detach(), "fake_score": fake_pred.mean().detach()}
 
     def _body_r1(self):
@@ -88,8 +90,7 @@ class GraphedRickAdapter(RickAdapter):
         self.d.zero_grad(set_to_none=True)
         (cfg.r1 / 2 * r1_loss * cfg.d_reg_every + 0 * real_pred[0]).backward()
         self._sync_grads(self.d_train)
-        self.masks_d.apply(self.d_named, force=True)
-        self.d_optim.step()
+        self._optim_step("d", True, force_masks=True)
         return {"r1": r1_loss.detach()}
 
     def _body_g(self):
@@ -101,8 +102,7 @@ class GraphedRickAdapter(RickAdapter):
         self.g.zero_grad(set_to_none=True)
         autograd.backward(g_loss, inputs=self.g_train)
         self._sync_grads(self.g_train)
-        self.masks_g.apply(self.g_named, force=True)
-        self.g_optim.step()
+        self._optim_step("g", True, force_masks=True)
         return {"g": g_loss.detach()}
 
     def _body_path(self):
@@ -118,13 +118,16 @@ class GraphedRickAdapter(RickAdapter):
             weighted = weighted + 0 * fake_img[0, 0, 0, 0]
         autograd.backward(weighted, inputs=self.g_train)
         self._sync_grads(self.g_train)
-        self.masks_g.apply(self.g_named, force=True)
-        self.g_optim.step()
+        self._optim_step("g", True, force_masks=True)
         self.mean_path_length.copy_(path_mean)
         return {"path": path_loss.detach(), "path_length": path_lengths.mean().detach()}
 
     def _body_ema(self):
-        self._ema()
+        if self.fused_optim:                            # one EMA-only launch per network
+            self.g_optim.ema_only()
+            self.d_optim.ema_only()
+        else:
+            self._ema()
         return {}
 
     # ---- capture / replay -------------------------------------------------------------------------------

@@ -244,3 +244,54 @@ def test_fused_generator_plan_on_cpu(cpu_stubbed, monkeypatch):
     want3, _ = mo.g_forward(gp, [z], size, noise=explicit)
     got3, _ = FG([z], noise=explicit)
     assert (got3 - want3).abs().max() < 1e-4 * want3.abs().max()
+
+
+# ------------------------------------------------------------------------------------------ checkpoints
+def test_checkpoint_round_trip_in_reference_format(tmp_path):
+    """rick_b200.checkpoint writes the reference's five keys (train:645-659); the file loads back, and -- when the
+    reference tree is present -- straight into the reference's own Generator / Discriminator with strict=True."""
+    import types
+    from rick_b200 import checkpoint, stylegan2 as sg
+    torch.manual_seed(0)
+    size = 32
+
+    def make():                                              # the attributes of RickAdapter that checkpoints touch
+        g, d, ge, de = sg.Generator(size, 512, 8), sg.Discriminator(size), sg.Generator(size, 512, 8), sg.Discriminator(size)
+        g_train = [p for n, p in g.named_parameters() if "convs" in n]
+        d_train = [p for n, p in d.named_parameters() if ("convs" in n and "convs.0" not in n) or "final" in n]
+        return types.SimpleNamespace(g=g, d=d, g_ema=ge, d_ema=de, g_train=g_train, d_train=d_train,
+                                     g_optim=torch.optim.Adam(g_train, lr=0.0016, betas=(0.0, 0.99 ** 0.8)),
+                                     d_optim=torch.optim.Adam(d_train, lr=0.0019, betas=(0.0, 0.99 ** (16 / 17))))
+    A = make()
+    nets = [A.g, A.d]
+    for p in A.g_train[:3] + A.d_train[:3]:                  # give the optimisers some state
+        p.grad = torch.randn_like(p)
+    A.g_optim.step(), A.d_optim.step()
+    path = tmp_path / "000100.pt"
+    checkpoint.save(path, A)
+    ckpt = torch.load(path, weights_only=False)
+    assert sorted(ckpt) == ["d", "d_optim", "g", "g_ema", "g_optim"]
+    assert all(v.is_contiguous() for v in ckpt["d"].values() if torch.is_tensor(v))
+    assert set(ckpt["g"]) == set(nets[0].state_dict()) and set(ckpt["d"]) == set(nets[1].state_dict())
+
+    B = make()
+    fresh = [B.g, B.d]
+    checkpoint.resume(path, B)
+    for k, v in A.g.state_dict().items():
+        assert torch.equal(B.g.state_dict()[k], v), k
+    for k, v in A.d.state_dict().items():
+        assert torch.equal(B.d_ema.state_dict()[k], v), k    # d_ema <- ckpt["d"] (train:879)
+    sa, sb = A.g_optim.state_dict(), B.g_optim.state_dict()
+    assert sa["param_groups"] == sb["param_groups"] and sorted(sa["state"]) == sorted(sb["state"])
+    for i in sa["state"]:
+        assert torch.equal(sa["state"][i]["exp_avg_sq"], sb["state"][i]["exp_avg_sq"])
+
+    from oracle import ref_loader
+    if ref_loader.available():                               # not on the GPU box
+        ref = ref_loader.load().model
+        rg, rd = ref.Generator(size, 512, 8), ref.Discriminator(size)
+        rg.load_state_dict(ckpt["g_ema"], strict=True)
+        rd.load_state_dict(ckpt["d"], strict=True)
+        # and the other direction: a reference-written state dict loads into this package's modules
+        fresh[0].load_state_dict(rg.state_dict(), strict=True)
+        fresh[1].load_state_dict(rd.state_dict(), strict=True)

@@ -72,7 +72,8 @@ ROWS_SHAPES = [
     # 0 / 1 / 4 (edge columns) / 6 / 31 (partial group), ragged last row tile, crops, 1024-px-D widths, down = 2
     (2, 3, 129, 129, 1, (1, 1)), (2, 3, 128, 128, 1, (2, 2)), (1, 2, 71, 73, 1, (1, 1)), (1, 2, 140, 101, 1, (2, 2)),
     (1, 2, 90, 98, 1, (-1, -2)), (1, 1, 513, 513, 1, (1, 1)), (1, 1, 40, 1025, 1, (2, 2)), (2, 3, 128, 128, 2, (1, 1)),
-    (1, 2, 257, 259, 2, (2, 2)), (1, 2, 150, 131, 2, (0, 3)), (3, 1, 67, 200, 1, (3, 0)),
+    (1, 2, 257, 259, 2, (2, 2)), (1, 2, 150, 131, 2, (0, 3)), (3, 1, 67, 200, 1, (3, 0)), (1, 1, 512, 512, 2, (1, 1)),
+    (1, 1, 100, 600, 1, (1, 1)), (1, 1, 90, 1000, 2, (2, 2)),
 ]
 
 

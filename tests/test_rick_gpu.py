@@ -141,3 +141,96 @@ def test_mask_apply_matches_reference_indexing():
     for k in params:
         assert np.array_equal(params[k].detach().cpu().numpy(), np_params[k]), k
         assert np.array_equal(params[k].grad.cpu().numpy(), np_grads[k]), k
+
+
+# ------------------------------------------------------------------------------------------ fused optimiser step
+def _adam_case(seed=0):
+    g = torch.Generator().manual_seed(seed)
+    shapes = {"convs.0.conv.weight": (1, 12, 8, 3, 3), "convs.0.conv.modulation.weight": (8, 16),
+              "convs.0.conv.modulation.bias": (8,), "convs.0.activate.bias": (12,), "style.1.weight": (16, 16),
+              "odd.weight": (5, 7)}
+    return {n: torch.randn(s, generator=g) for n, s in shapes.items()}
+
+
+def test_fused_masked_adam_matches_masks_plus_torch_adam_plus_ema():
+    """rick_adam_mask_ema == rick_mask_apply semantics + torch.optim.Adam + accumulate(), over several steps."""
+    from rick_b200.optim import FusedMaskedAdam
+
+    class _Masks:
+        def __init__(self, state, zero):
+            self.state, self.zero = state, zero
+
+    init = _adam_case()
+    trainable = [n for n in init if n.startswith("convs") or n.startswith("odd")]
+    gen = torch.Generator().manual_seed(1)
+    state = {"convs.0.conv.weight": torch.tensor([1, 0, 4, 3, 0, 1, 4, 4, 0, 2, 1, 0], dtype=torch.uint8),
+             "convs.0.conv.modulation.weight": torch.tensor([0, 1, 3, 4, 0, 0, 1, 4], dtype=torch.uint8)}
+    state["convs.0.conv.modulation.bias"] = state["convs.0.conv.modulation.weight"].clone()
+    zero = {k: ((v & 2) > 0).to(torch.uint8) for k, v in state.items()}
+    zero["convs.0.conv.weight"][4] = 1                       # pruned in an earlier round, not in this one
+    decay, lr, betas = 0.5 ** (32 / 10000), 0.002 * 4 / 5, (0.0, 0.99 ** (4 / 5))
+
+    # --- reference composition on CPU (float32, torch.optim.Adam single-tensor path)
+    ref = {n: torch.nn.Parameter(v.clone()) for n, v in init.items()}
+    ref_ema = {n: v.clone() + 0.25 for n, v in init.items()}
+    opt = torch.optim.Adam([ref[n] for n in trainable], lr=lr, betas=betas)
+    # --- fused path
+    dev = {n: torch.nn.Parameter(v.clone().cuda()) for n, v in init.items()}
+    dev_ema = {n: torch.nn.Parameter((v.clone() + 0.25).cuda()) for n, v in init.items()}
+    masks = _Masks({k: v.cuda() for k, v in state.items()}, {k: v.cuda() for k, v in zero.items()})
+    fopt = FusedMaskedAdam(dev, [dev[n] for n in trainable], lr=lr, betas=betas, masks=masks, ema_named=dev_ema,
+                           ema_decay=decay)
+    for step in range(4):
+        grads = {n: torch.randn(init[n].shape, generator=gen) * 10 ** (-step) for n in trainable}
+        use_masks = step > 0
+        for n in trainable:
+            ref[n].grad = grads[n].clone()
+            dev[n].grad = grads[n].clone().cuda()
+        if use_masks:
+            with torch.no_grad():
+                for n, st in state.items():
+                    p = ref[n]
+                    rows = p.view(st.numel(), -1)
+                    grows = p.grad.view(st.numel(), -1)
+                    z = zero[n].bool()
+                    grows[(st & 1).bool() | z] = 0
+                    rows[z] = 0
+        opt.step()
+        with torch.no_grad():
+            for n in init:
+                ref_ema[n].mul_(decay).add_(ref[n].detach(), alpha=1 - decay)
+        fopt.step(apply_masks=use_masks, ema=True)
+    for n in init:
+        torch.testing.assert_close(dev[n].detach().cpu(), ref[n].detach(), rtol=2e-6, atol=1e-7, msg=n)
+        torch.testing.assert_close(dev_ema[n].detach().cpu(), ref_ema[n], rtol=2e-6, atol=1e-7, msg=n)
+    # masks are exact: pruned filters are exactly zero, frozen filters did not move after masking started
+    w = dev["convs.0.conv.weight"].detach().cpu().view(12, -1)
+    assert (w[zero["convs.0.conv.weight"].bool()] == 0).all()
+    # untouched (non-trainable) parameter: bit-identical
+    assert torch.equal(dev["style.1.weight"].detach().cpu(), init["style.1.weight"])
+    # optimiser state moves into torch.optim.Adam unchanged
+    sd = fopt.state_dict()
+    opt2 = torch.optim.Adam([torch.nn.Parameter(init[n].clone().cuda()) for n in trainable], lr=1.0)
+    opt2.load_state_dict(sd)
+    assert opt2.param_groups[0]["lr"] == pytest.approx(lr) and float(opt2.state_dict()["state"][0]["step"]) == 4
+    fopt2 = FusedMaskedAdam(dev, [dev[n] for n in trainable], lr=1.0, betas=(0.5, 0.5))
+    fopt2.load_state_dict(opt.state_dict())
+    assert fopt2.lr == pytest.approx(lr) and fopt2.steps.tolist() == [4.0] * len(trainable)
+    torch.testing.assert_close(fopt2.exp_avg_sq[id(dev[trainable[0]])].cpu(),
+                               opt.state_dict()["state"][0]["exp_avg_sq"], rtol=0, atol=0)
+
+
+def test_fused_masked_adam_ema_only_and_channels_last():
+    from rick_b200.optim import FusedMaskedAdam
+    g = torch.Generator().manual_seed(3)
+    w = torch.randn(16, 8, 3, 3, generator=g)
+    p = torch.nn.Parameter(w.cuda().to(memory_format=torch.channels_last))
+    e = torch.nn.Parameter((w * 0.5).cuda().to(memory_format=torch.channels_last))
+    opt = FusedMaskedAdam({"convs.1.0.weight": p}, [p], lr=0.01, betas=(0.0, 0.99), ema_named={"convs.1.0.weight": e},
+                          ema_decay=0.9)
+    opt.ema_only()
+    torch.testing.assert_close(e.detach().cpu(), w * 0.5 * 0.9 + w * 0.1, rtol=1e-6, atol=1e-7)
+    assert float(opt.steps.sum()) == 0 and torch.equal(p.detach().cpu(), w)
+    p.grad = torch.randn(16, 8, 3, 3, generator=g).cuda()          # contiguous gradient for a channels-last weight
+    with pytest.raises(RuntimeError, match="memory layout"):
+        opt.step()
