@@ -197,6 +197,9 @@ def run_ours(args):
             adapter._real.copy_(shots_dev[:batch])
             for key in ("d", "r1", "g", "path", "ema"):
                 adapter._run(key)
+            # graph capture empties the caching allocator (torch.cuda.graph does gc + empty_cache): let the eager
+            # Fisher round re-acquire its working set once here, as part of the warm-up, not inside the timed steps
+            adapter.fisher_round(fisher_lat, shots_dev[:cfg.num_fisher_img])
     except Exception as exc:                       # graph capture refused: fall back to the eager executor, say so
         if mode != "graphs" or args.mode == "graphs":
             raise
@@ -339,6 +342,30 @@ def op_sweep(device):
     out["d_blur_pad22_128->129"] = 4 * n * c * (128 * 128 + 129 * 129) / ms / 1e6
     ms = _time_kernel(lambda: op.upfirdn2d(x, taps1, down=2, pad=(1, 1)), flush, iters=5)
     out["down2_128->64"] = 4 * n * c * (128 * 128 + 64 * 64) / ms / 1e6
+    del x
+    # bf16 storage (fp32 accumulate): same element counts, half the bytes
+    xh = torch.randn(n, c, 128, 128, device=device, dtype=torch.bfloat16)
+    ms = _time_kernel(lambda: op.upfirdn2d(xh, taps4, up=2, pad=(2, 1)), flush, iters=5)
+    out["bf16_upfirdn2d_up2_128->256"] = 2 * n * c * 5 * 128 * 128 / ms / 1e6
+    ms = _time_kernel(lambda: op.upfirdn2d(xh, taps1, pad=(2, 2)), flush, iters=5)
+    out["bf16_d_blur_pad22_128->129"] = 2 * n * c * (128 * 128 + 129 * 129) / ms / 1e6
+    bh = torch.randn(c, device=device, dtype=torch.bfloat16)
+    ms = _time_kernel(lambda: op.fused_leaky_relu(xh, bh), flush, iters=5)
+    out["bf16_bias_act_fwd_128"] = 2 * 2 * xh.numel() / ms / 1e6
+    del xh
+    # the 12x12 antialiasing filter of non_leaking.py:338, 359 (generic kernel; small, latency-bound tensors)
+    sym6 = torch.tensor([0.015404109327027373, 0.0034907120842174702, -0.11799011114819057, -0.048311742585633,
+                         0.4910559419267466, 0.787641141030194, 0.3379294217276218, -0.07263752278646252,
+                         -0.021060292512300564, 0.04472490177066578, 0.0017677118642428036, -0.007800708325034148],
+                        device=device)
+    k12 = torch.outer(sym6, sym6)
+    xa = torch.randn(8, 3, 282, 282, device=device)
+    ms = _time_kernel(lambda: op.upfirdn2d(xa, k12, up=2), flush, iters=5)
+    ya = op.upfirdn2d(xa, k12, up=2)
+    out["aug_sym6_up2_282"] = 4 * (xa.numel() + ya.numel()) / ms / 1e6
+    ms = _time_kernel(lambda: op.upfirdn2d(ya, k12, down=2), flush, iters=5)
+    out["aug_sym6_down2_553"] = 4 * (ya.numel() + ya.numel() // 4) / ms / 1e6
+    del xa, ya
     from rick_b200 import conv_tc as ct
     xn = torch.randn(n, 129, 129, c, device=device)                       # NHWC blur after the transposed conv
     ms = _time_kernel(lambda: ct.blur_nhwc(xn, taps4, (1, 1)), flush, iters=5)

@@ -116,6 +116,25 @@ def g_path_regularize(fake_img, latents, mean_path_length, noise, decay=0.01):
     return path_penalty, path_mean.detach(), path_lengths
 
 
+def d_pair(d, fake: torch.Tensor, real: torch.Tensor):
+    """``d(fake)[0], d(real)[0]`` in ONE pass over the discriminator (half the launches of the D step, the weights
+    scaled once).  The only cross-sample coupling in D is the minibatch standard deviation (model_probe_tune.py:749-756):
+    a call on B samples splits them into ``group = min(B, 25)`` members x ``M = B / group`` groups, sample ``j*M + m``
+    being member j of group m.  Stacking the two batches as [fake[jM:(j+1)M], real[jM:(j+1)M] for j in range(group)]
+    and keeping ``group`` makes the 2M groups of the joint call exactly the M fake groups and the M real groups."""
+    b = fake.shape[0]
+    if real.shape[0] != b:
+        return d(fake)[0], d(real)[0]
+    group = min(b, d.stddev_group)
+    if b % group != 0:
+        return d(fake)[0], d(real)[0]
+    m = b // group
+    x = torch.stack([fake.reshape(group, m, *fake.shape[1:]), real.reshape(group, m, *real.shape[1:])], dim=1)
+    pred, _ = d(x.reshape(2 * b, *fake.shape[1:]), stddev_group=group)
+    pred = pred.reshape(group, 2, m, *pred.shape[1:])
+    return pred[:, 0].reshape(b, *pred.shape[3:]), pred[:, 1].reshape(b, *pred.shape[3:])
+
+
 class RickAdapter:
     """Owns the four networks, the two Adam optimisers, the Fisher accumulators and the filter masks."""
 
@@ -166,34 +185,38 @@ class RickAdapter:
     def fisher_round(self, latents: torch.Tensor, reals: torch.Tensor, layer_noise: Optional[list] = None):
         """train:214-393.  ``latents`` (num_fisher_img, latent) are the reference's ``_noise/000j.pt`` rows,
         ``reals`` (num_fisher_img, 3, H, W) the first image of each loader batch."""
-        cfg = self.cfg
+        mine = self._fisher_begin(latents.shape[0])
+        for j in mine:
+            self._fisher_image(latents[j:j + 1], reals[j:j + 1], None if layer_noise is None else layer_noise[j])
+        self._fisher_end()
+
+    def _fisher_begin(self, n_images: int):
         for m in (self.g_ema, self.d_ema):
             for p in m.parameters():
                 p.requires_grad_(True)
             m.eval()
-        self.acc_g.reset()
-        self.acc_d.reset()
-        g_params = list(self.g_ema.parameters())
-        d_params = list(self.d_ema.parameters())
+        self.acc_g.zero()
+        self.acc_d.zero()
         world = rdist.world_size()
         rank = torch.distributed.get_rank() if world > 1 else 0
-        mine = rdist.shard_range(latents.shape[0], rank, world)     # Fisher images are sharded over ranks
-        for j in mine:
-            noise = None if layer_noise is None else layer_noise[j]
-            fake, _ = self.g_ema([latents[j:j + 1]], noise=noise)
-            fake_pred, _ = self.d_ema(fake)
-            real_pred, _ = self.d_ema(reals[j:j + 1])
-            g_loss = g_nonsaturating_loss(fake_pred)
-            d_loss = d_logistic_loss(real_pred, fake_pred)
-            g_grads = autograd.grad(g_loss, g_params, retain_graph=True)
-            d_grads = autograd.grad(d_loss, d_params)
-            self.acc_g.add(g_grads)
-            self.acc_d.add(d_grads)
-        if world > 1:                                  # one exchange step: SUM of the grad^2 accumulators
+        return rdist.shard_range(n_images, rank, world)            # Fisher images are sharded over ranks
+
+    def _fisher_image(self, latent: torch.Tensor, real: torch.Tensor, noise=None):
+        """grad**2 of one (latent, real image) pair into the accumulators (train:225-263).  The two discriminator calls
+        of the reference share one pass (d_pair; at batch 1 each sample is its own minibatch-stddev group)."""
+        fake, _ = self.g_ema([latent], noise=noise)
+        fake_pred, real_pred = d_pair(self.d_ema, fake, real)
+        g_loss = g_nonsaturating_loss(fake_pred)
+        d_loss = d_logistic_loss(real_pred, fake_pred)
+        g_grads = autograd.grad(g_loss, list(self.g_ema.parameters()), retain_graph=True)
+        d_grads = autograd.grad(d_loss, list(self.d_ema.parameters()))
+        self.acc_g.add(g_grads, first=False)
+        self.acc_d.add(d_grads, first=False)
+
+    def _fisher_end(self):
+        cfg = self.cfg
+        if rdist.world_size() > 1:                     # one exchange step: SUM of the grad^2 accumulators
             for acc in (self.acc_g, self.acc_d):
-                if acc.count == 0:
-                    for t in acc.acc:
-                        t.zero_()
                 rdist.allreduce_sum_(acc.acc)
         div = cfg.num_fisher_img * cfg.batch          # the reference's divisor (train:267), kept as is
         self.acc_g.average(div)
@@ -225,12 +248,13 @@ class RickAdapter:
                 fake_img, _ = self.fg(z, inject_index=inject, noise=noise_of(cfg.batch))
             else:
                 fake_img, _ = self.g(z, inject_index=inject, noise=noise_of(cfg.batch))
-        fake_pred, _ = self.d(fake_img)
-        real_pred, _ = self.d(real_img)
+        fake_pred, real_pred = d_pair(self.d, fake_img, real_img)
         d_loss = d_logistic_loss(real_pred, fake_pred)
         out["d"], out["real_score"], out["fake_score"] = d_loss.detach(), real_pred.mean().detach(), fake_pred.mean().detach()
         self.d.zero_grad(set_to_none=True)
-        d_loss.backward()
+        # only the trainable subset needs gradients (train:921-931 hands exactly these to the optimiser); asking for
+        # them alone skips the from-RGB weight gradient and everything upstream of it
+        autograd.backward(d_loss, inputs=[p for p in self.d_train if p.requires_grad])
         self._sync_grads(self.d_train)
         r1_iter = i % cfg.d_reg_every == 0
         path_iter = i % cfg.g_reg_every == 0 and after_warmup
@@ -245,7 +269,8 @@ class RickAdapter:
             real_pred = real_pred.view(real_r.size(0), -1).mean(dim=1).unsqueeze(1)
             r1_loss = d_r1_loss(real_pred, real_r)
             self.d.zero_grad(set_to_none=True)
-            (cfg.r1 / 2 * r1_loss * cfg.d_reg_every + 0 * real_pred[0]).backward()
+            autograd.backward(cfg.r1 / 2 * r1_loss * cfg.d_reg_every + 0 * real_pred[0],
+                              inputs=[p for p in self.d_train if p.requires_grad])
             self._sync_grads(self.d_train)
             self._optim_step("d", after_warmup, ema=True)
             out["r1"] = r1_loss.detach()

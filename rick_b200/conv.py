@@ -26,6 +26,79 @@ from .op import styled as _styled
 _FORCE = os.environ.get("RICK_CONV_BACKEND", "")   # "", "cudnn" or "tc" (tests use it to pin an executor)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# library convolution with explicit first- and second-order gradients
+# ---------------------------------------------------------------------------------------------------------------
+# R1 (train:462-493) and the path-length regulariser (train:546-589) differentiate THROUGH a backward pass.  Left to
+# autograd's generic double-backward formula, the weight-gradient term of a convolution is evaluated as a forward
+# convolution whose "filter" is a whole feature map (a (128, 1, 256, 256) input against a (128, 1, 256, 256) weight at
+# 256 px): the library has no tensor-core kernel for that and one path-length iteration spent 10 of its 33 ms there
+# (round-1 torch.profiler run, scripts/profile_path.py).  Written out, every term of the second derivative is again a
+# forward conv, a data gradient or a weight gradient with ordinary shapes:
+#     y  = conv(x, w)          gx = dgrad(g, w)          gw = wgrad(g, x)
+#     d<ggx, gx>/dg = conv(ggx, w)      d<ggx, gx>/dw = wgrad(g, ggx)
+#     d<ggw, gw>/dg = conv(x, ggw)      d<ggw, gw>/dx = dgrad(g, ggw)
+# so the two Functions below call themselves / each other and stay differentiable to any order.
+def _conv_args(stride: int, padding: int, transposed: bool):
+    return [stride, stride], [padding, padding], [1, 1], transposed, [0, 0], 1
+
+
+class _Conv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, stride, padding, transposed):
+        ctx.save_for_backward(x, w)
+        ctx.cfg = (stride, padding, transposed)
+        return torch.ops.aten.convolution(x, w, None, *_conv_args(stride, padding, transposed))
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not torch.is_grad_enabled():                    # plain backward (no create_graph): straight to the library
+            gx, gw, _ = torch.ops.aten.convolution_backward(g, x, w, None, *_conv_args(*ctx.cfg),
+                                                            [bool(need_x), bool(need_w), False])
+            return gx, gw, None, None, None
+        gx, gw = _ConvGrad.apply(g, x, w, need_x, need_w, *ctx.cfg)
+        return gx, gw, None, None, None
+
+
+class _ConvGrad(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, g, x, w, need_x, need_w, stride, padding, transposed):
+        ctx.save_for_backward(g, x, w)
+        ctx.cfg = (stride, padding, transposed)
+        gx, gw, _ = torch.ops.aten.convolution_backward(g, x, w, None, *_conv_args(stride, padding, transposed),
+                                                        [bool(need_x), bool(need_w), False])
+        ctx.have = (bool(need_x), bool(need_w))
+        return gx, gw                                      # None for a gradient that was not asked for
+
+    @staticmethod
+    def backward(ctx, ggx, ggw):
+        g, x, w = ctx.saved_tensors
+        cfg = ctx.cfg
+        have_x, have_w = ctx.have
+        ggx = ggx if have_x else None
+        ggw = ggw if have_w else None
+        need_g, need_x, need_w = ctx.needs_input_grad[:3]
+        d_g = d_x = d_w = None
+        if need_g:
+            if ggx is not None:
+                d_g = _Conv.apply(ggx, w, *cfg)
+            if ggw is not None:
+                t = _Conv.apply(x, ggw, *cfg)
+                d_g = t if d_g is None else d_g + t
+        if need_w and ggx is not None:
+            d_w = _ConvGrad.apply(g, ggx, w, False, True, *cfg)[1]
+        if need_x and ggw is not None:
+            d_x = _ConvGrad.apply(g, x, ggw, True, False, *cfg)[0]
+        return d_g, d_x, d_w, None, None, None, None, None
+
+
+def _lib_conv(x, w, stride: int = 1, padding: int = 0, transposed: bool = False):
+    """``F.conv2d`` / ``F.conv_transpose2d`` (groups 1, no bias) with the gradient structure above."""
+    return _Conv.apply(x, w, stride, padding, transposed)
+
+
 def _require_cuda(x: torch.Tensor, what: str):
     if not x.is_cuda:
         raise RuntimeError(f"rick_b200.conv.{what}: input must be a CUDA tensor (no CPU fallback in this package)")
@@ -54,7 +127,8 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
         extra = 4 - ci % 4
         x = F.pad(x, (0, 0, 0, 0, 0, extra))
         weight = F.pad(weight, (0, 0, 0, 0, 0, extra))
-    return F.conv2d(x, weight, bias=bias, stride=stride, padding=padding)
+    out = _lib_conv(x, weight, stride, padding)
+    return out if bias is None else out + bias.reshape(1, -1, 1, 1)
 
 
 def modulated_conv2d(x: torch.Tensor, w: torch.Tensor, s: torch.Tensor, demod: Optional[torch.Tensor],
@@ -80,20 +154,20 @@ def modulated_conv2d(x: torch.Tensor, w: torch.Tensor, s: torch.Tensor, demod: O
         noise, noise_weight, bias, slope, act_scale = epilogue
         xm = _styled.modulate(x, s)
         if upsample:
-            out = blur(F.conv_transpose2d(xm, w.transpose(0, 1), stride=2, padding=0))
+            out = blur(_lib_conv(xm, w.transpose(0, 1), 2, 0, True))
         else:
-            out = F.conv2d(xm, w, padding=padding)
+            out = _lib_conv(xm, w, 1, padding)
         if noise is None:
             noise = out.new_empty(out.shape[0], 1, out.shape[2], out.shape[3]).normal_()
         return _styled.styled_epilogue(out, demod, noise, noise_weight, bias, slope, act_scale)
     xm = x * s[:, :, None, None]
     if upsample:
-        out = F.conv_transpose2d(xm, w.transpose(0, 1), stride=2, padding=0)
+        out = _lib_conv(xm, w.transpose(0, 1), 2, 0, True)
         out = blur(out)
     elif downsample:
-        out = F.conv2d(blur(xm), w, stride=2, padding=0)
+        out = _lib_conv(blur(xm), w, 2, 0)
     else:
-        out = F.conv2d(xm, w, padding=padding)
+        out = _lib_conv(xm, w, 1, padding)
     if demod is not None:
         out = out * demod[:, :, None, None]
     return out

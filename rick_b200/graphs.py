@@ -25,7 +25,8 @@ import torch
 from torch import autograd, optim
 
 from . import dist as rdist
-from .adapt import (AdaptConfig, RickAdapter, d_logistic_loss, d_r1_loss, g_nonsaturating_loss, g_path_regularize)
+from .adapt import (AdaptConfig, RickAdapter, d_logistic_loss, d_pair, d_r1_loss, g_nonsaturating_loss,
+                    g_path_regularize)
 from .fused import FusedGenerator
 
 
@@ -47,6 +48,8 @@ class GraphedRickAdapter(RickAdapter):
         dev = self.device
         self.fg = FusedGenerator(generator) if (fused_generator and FusedGenerator.supports(generator)) else None
         self._real = torch.zeros(cfg.batch, 3, cfg.size, cfg.size, device=dev)
+        self._f_lat = torch.zeros(1, cfg.latent, device=dev)
+        self._f_real = torch.zeros(1, 3, cfg.size, cfg.size, device=dev)
         self._inject = {k: torch.full((), generator.n_latent, dtype=torch.long, device=dev) for k in ("d", "g", "path")}
         self._layer = torch.arange(generator.n_latent, device=dev).view(1, -1, 1)
         self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}
@@ -72,11 +75,10 @@ class GraphedRickAdapter(RickAdapter):
                 fake_img, _ = self.fg([latent], input_is_latent=True)
             else:
                 fake_img, _ = self.g([latent], input_is_latent=True)
-        fake_pred, _ = self.d(fake_img)
-        real_pred, _ = self.d(self._real)
+        fake_pred, real_pred = d_pair(self.d, fake_img, self._real)
         d_loss = d_logistic_loss(real_pred, fake_pred)
         self.d.zero_grad(set_to_none=True)
-        d_loss.backward()
+        autograd.backward(d_loss, inputs=self.d_train)
         self._sync_grads(self.d_train)
         self._optim_step("d", True, force_masks=True)
         return {"d": d_loss.detach(), "real_score": real_pred.mean().detach(), "fake_score": fake_pred.mean().detach()}
@@ -88,7 +90,7 @@ class GraphedRickAdapter(RickAdapter):
         real_pred = real_pred.view(real_r.size(0), -1).mean(dim=1).unsqueeze(1)
         r1_loss = d_r1_loss(real_pred, real_r)
         self.d.zero_grad(set_to_none=True)
-        (cfg.r1 / 2 * r1_loss * cfg.d_reg_every + 0 * real_pred[0]).backward()
+        autograd.backward(cfg.r1 / 2 * r1_loss * cfg.d_reg_every + 0 * real_pred[0], inputs=self.d_train)
         self._sync_grads(self.d_train)
         self._optim_step("d", True, force_masks=True)
         return {"r1": r1_loss.detach()}
@@ -131,7 +133,27 @@ class GraphedRickAdapter(RickAdapter):
         return {}
 
     # ---- capture / replay -------------------------------------------------------------------------------
-    def _run(self, key: str):
+    def _body_fisher(self):
+        self._fisher_image(self._f_lat, self._f_real)
+        return {}
+
+    def fisher_round(self, latents: torch.Tensor, reals: torch.Tensor, layer_noise=None):
+        """The Fisher round with its per-image body (G forward, joint D pass, two backward passes, grad**2 accumulation)
+        replayed from a CUDA graph; the exchange step and the mask update stay eager.  Explicit per-layer noise (parity
+        tests) takes the eager path."""
+        if layer_noise is not None:
+            return super().fisher_round(latents, reals, layer_noise)
+        mine = self._fisher_begin(latents.shape[0])
+        self._ensure("fisher")                          # capture (with its warm-up executions) BEFORE clearing
+        self.acc_g.zero()
+        self.acc_d.zero()
+        for j in mine:
+            self._f_lat.copy_(latents[j:j + 1], non_blocking=True)
+            self._f_real.copy_(reals[j:j + 1], non_blocking=True)
+            self._run("fisher")
+        self._fisher_end()
+
+    def _ensure(self, key: str):
         if key not in self._graphs:
             body = getattr(self, "_body_" + key)
             side = torch.cuda.Stream()
@@ -147,6 +169,9 @@ class GraphedRickAdapter(RickAdapter):
                 outs = body()
             self._graph_launches[key] = int(_lib.lib().rick_launch_count() - n0)   # launches recorded, not executed
             self._graphs[key], self._outs[key] = graph, outs
+
+    def _run(self, key: str):
+        self._ensure(key)
         self._graphs[key].replay()
         self.replayed_launches += self._graph_launches[key]
         return self._outs[key]

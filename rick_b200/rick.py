@@ -51,8 +51,14 @@ class FisherAccumulator:
     def reset(self):
         self.count = 0
 
-    def add(self, grads: Sequence[torch.Tensor]):
-        """acc (+)= grad ** 2 for every parameter; ``grads`` is what ``autograd.grad(loss, params)`` returned."""
+    def zero(self):
+        """Explicitly clear the accumulators (for callers that always accumulate, e.g. a captured CUDA graph)."""
+        torch._foreach_zero_(self.acc)
+        self.count = 0
+
+    def add(self, grads: Sequence[torch.Tensor], first: Optional[bool] = None):
+        """acc (+)= grad ** 2 for every parameter; ``grads`` is what ``autograd.grad(loss, params)`` returned.
+        ``first`` overrides "overwrite on the first call after reset()" (False = always accumulate)."""
         if len(grads) != len(self.acc):
             raise RuntimeError("FisherAccumulator.add: gradient list does not match the parameter list")
         keep = [g.detach().contiguous() for g in grads]       # alive until the launch is enqueued
@@ -61,7 +67,7 @@ class FisherAccumulator:
                 raise RuntimeError("FisherAccumulator.add: gradient shape / dtype / device mismatch")
         with torch.cuda.device(self.acc[0].device):
             st = _lib.lib().rick_fisher_accum(self._acc_tab, _lib.ptr_table([g.data_ptr() for g in keep]), self._numel,
-                                              len(keep), int(self.count == 0), _stream())
+                                              len(keep), int(self.count == 0 if first is None else first), _stream())
         _lib.check(st, "rick_fisher_accum")
         self.count += 1
 

@@ -408,14 +408,16 @@ class Discriminator(nn.Module):
     def estimate_fisher(self, loglikelihood):
         return _estimate_fisher(self, loglikelihood)
 
-    def forward(self, inp, ind=None, real=False):
+    def forward(self, inp, ind=None, real=False, stddev_group=None):
+        """``stddev_group``: override of ``min(batch, self.stddev_group)`` for the minibatch-stddev grouping -- used by
+        rick_b200.adapt.d_pair to score two batches in one pass with each batch's own statistics."""
         feat: list = []
         out = self.convs[0](_fmt(inp))
         feat.append(out)
         for block in list(self.convs)[1:]:
             out = block(out, feat)          # conv1 / conv2 evaluated ONCE (see module docstring)
         batch, channel, height, width = out.shape
-        group = min(batch, self.stddev_group)
+        group = min(batch, self.stddev_group) if stddev_group is None else stddev_group
         stddev = out.view(group, -1, self.stddev_feat, channel // self.stddev_feat, height, width)
         stddev = torch.sqrt(stddev.var(0, unbiased=False) + 1e-8)
         stddev = stddev.mean([2, 3, 4], keepdims=True).squeeze(2)

@@ -127,3 +127,74 @@ def test_1024px_architecture_runs_one_round_and_iteration():
     out = A.step(0, real, DrawStream(1, "cuda", cpu_seeded=False))
     assert {"d", "g", "r1", "path"} <= set(out)
     assert all(torch.isfinite(v).all() for v in out.values())
+
+
+def test_graphed_adapter_replays_the_eager_iteration_and_fisher_round():
+    """GraphedRickAdapter (CUDA-graph replay, the bench's default executor) against the eager RickAdapter on identical
+    weights and draws.  Per-layer noise is neutralised (zero noise strengths) and style mixing / regularisers are off so
+    both executors see the same random inputs; the graph's capture-time warm-up steps are rolled back before comparing."""
+    from rick_b200 import stylegan2 as sg
+    from rick_b200.adapt import AdaptConfig, DrawStream, RickAdapter
+    from rick_b200.graphs import GraphedRickAdapter
+    size = 32
+    cfg = AdaptConfig(size=size, batch=2, warmup_iter=0, mixing=0.0, num_fisher_img=2, d_reg_every=10 ** 6,
+                      g_reg_every=10 ** 6)
+    gp, dp = synth.g_state(size, 1), synth.d_state(size, 2)
+    gp = {k: (torch.zeros_like(v) if k.endswith("noise.weight") else v) for k, v in gp.items()}
+
+    def nets():
+        G, Ge, D, De = sg.Generator(size, 512, 8), sg.Generator(size, 512, 8), sg.Discriminator(size), sg.Discriminator(size)
+        G.load_state_dict(gp), Ge.load_state_dict(gp), D.load_state_dict(dp), De.load_state_dict(dp)
+        return G.cuda(), D.cuda(), Ge.cuda(), De.cuda()
+
+    class Det(GraphedRickAdapter):                        # latents come from buffers the test fills
+        def _latent(self, batch, key):
+            return self.g.style(self._z[key][:batch]).unsqueeze(1).repeat(1, self.g.n_latent, 1)
+
+    eager = RickAdapter(cfg, *nets())
+    graphed = Det(cfg, *nets(), fused_generator=False)    # same generator executor as the eager adapter
+    graphed._z = {k: torch.zeros(cfg.batch, 512, device="cuda") for k in ("d", "g", "path")}
+    shots = synth.shots(4, size, 0).cuda()
+    lat = synth.latents(2, 9).cuda()
+
+    # ---- capture everything, then roll the capture-time warm-up steps back
+    graphed._real.copy_(shots[:2])
+    graphed._fisher_begin(2)
+    for key in ("fisher", "d", "g", "ema"):
+        graphed._ensure(key)
+    with torch.no_grad():
+        for net, sd in ((graphed.g, gp), (graphed.g_ema, gp), (graphed.d, dp), (graphed.d_ema, dp)):
+            for k, v in net.state_dict().items():
+                v.copy_(sd[k])
+    for opt in (graphed.g_optim, graphed.d_optim):
+        opt.steps.zero_()
+        for t in list(opt.exp_avg.values()) + list(opt.exp_avg_sq.values()):
+            t.zero_()
+
+    # ---- Fisher round: grad**2 accumulators and masks
+    eager.fisher_round(lat, shots[:2])
+    graphed.fisher_round(lat, shots[:2])
+    for name, a, b in zip(eager.acc_g.names, eager.acc_g.acc, graphed.acc_g.acc):
+        if not name.endswith("noise.weight"):            # d loss / d noise strength depends on the noise draw itself
+            torch.testing.assert_close(b, a, rtol=2e-2, atol=1e-12, msg=name)
+    for name, a, b in zip(eager.acc_d.names, eager.acc_d.acc, graphed.acc_d.acc):
+        torch.testing.assert_close(b, a, rtol=2e-2, atol=1e-12, msg=name)
+    fe, fg = eager.masks_g.index_sets()[0], graphed.masks_g.index_sets()[0]
+    same = sum(len(np.intersect1d(fe[k], fg[k])) for k in fe)
+    assert same >= 0.99 * sum(len(v) for v in fe.values())
+
+    # ---- one iteration with the same latents and real images
+    draws = DrawStream(5, "cuda")
+    probe = DrawStream(5, "cuda")
+    graphed._z["d"].copy_(probe.mixing_latents(cfg.batch, cfg.latent, 0.0)[0])
+    graphed._z["g"].copy_(probe.mixing_latents(cfg.batch, cfg.latent, 0.0)[0])
+    oe = eager.step(1, shots[2:4], draws)
+    og = graphed.step(1, shots[2:4])
+    for k in ("d", "g"):
+        torch.testing.assert_close(og[k], oe[k], rtol=2e-3, atol=2e-3, msg=k)
+    ne, ng = dict(eager.d.named_parameters()), dict(graphed.d.named_parameters())
+    for k in ("convs.1.conv1.0.weight", "final_linear.1.weight"):
+        torch.testing.assert_close(ng[k], ne[k], rtol=1e-3, atol=1e-4, msg=k)
+    ge, gg = dict(eager.g_ema.named_parameters()), dict(graphed.g_ema.named_parameters())
+    torch.testing.assert_close(gg["convs.1.conv.weight"], ge["convs.1.conv.weight"], rtol=1e-3, atol=1e-5)
+    assert graphed.replayed_launches > 0

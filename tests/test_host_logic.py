@@ -295,3 +295,35 @@ def test_checkpoint_round_trip_in_reference_format(tmp_path):
         # and the other direction: a reference-written state dict loads into this package's modules
         fresh[0].load_state_dict(rg.state_dict(), strict=True)
         fresh[1].load_state_dict(rd.state_dict(), strict=True)
+
+
+# ------------------------------------------------------------------------------------------ conv gradient structure
+@pytest.mark.parametrize("transposed,stride,padding", [(False, 1, 1), (False, 2, 0), (True, 2, 0)])
+def test_lib_conv_first_and_second_order_match_autograd(transposed, stride, padding):
+    """rick_b200.conv._lib_conv spells out dgrad / wgrad and their derivatives (so R1 / path-length never hit autograd's
+    feature-map-sized-filter double-backward); every order must equal what autograd derives for F.conv2d itself."""
+    from torch.nn import functional as F
+    from rick_b200.conv import _lib_conv
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 4, 9, 9, dtype=torch.double, generator=g).requires_grad_(True)
+    w = torch.randn(6, 4, 3, 3, dtype=torch.double, generator=g).requires_grad_(True)
+
+    def ref(x, w):
+        if transposed:
+            return F.conv_transpose2d(x, w.transpose(0, 1), stride=stride, padding=padding)
+        return F.conv2d(x, w, stride=stride, padding=padding)
+
+    def new(x, w):
+        return _lib_conv(x, w.transpose(0, 1) if transposed else w, stride, padding, transposed)
+
+    res = []
+    for f in (ref, new):
+        y = f(x, w)
+        gx, gw = torch.autograd.grad((y ** 2).sum(), [x, w], create_graph=True)
+        ramp = torch.arange(gw.numel(), dtype=torch.double).view_as(gw)
+        ggx, ggw = torch.autograd.grad((gx ** 3).sum() + (gw ** 2 * ramp).sum(), [x, w])
+        (gx_only,) = torch.autograd.grad((f(x, w) ** 2).sum(), [x], create_graph=True)     # the path-length pattern
+        (gw_from_gx,) = torch.autograd.grad((gx_only ** 2).sum(), [w])
+        res.append((y.detach(), gx.detach(), gw.detach(), ggx, ggw, gw_from_gx))
+    for a, b in zip(*res):
+        torch.testing.assert_close(a, b, rtol=1e-10, atol=1e-10)

@@ -148,3 +148,27 @@ def test_r1_and_path_length_second_order_vs_golden(golden):
     np.testing.assert_allclose(plen.detach().cpu().numpy(), gold["path_lengths"], rtol=5e-2)
     pl.backward()                                            # double backward through G runs
     assert all(torch.isfinite(p.grad).all() for n, p in G.named_parameters() if "convs" in n and p.grad is not None)
+
+
+@pytest.mark.parametrize("batch", [2, 3, 50])
+def test_d_pair_equals_two_discriminator_calls(batch):
+    """One joint pass over D scores (fake, real) exactly as two separate calls do: the chunk-interleaved stacking keeps
+    every minibatch-stddev group inside its own batch (group = min(B, 25): B = 50 -> 25 members x 2 groups)."""
+    from rick_b200.adapt import d_pair
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        _, D, _, _ = _build(32, 11, 12)
+        fake = synth.shots(batch, 32, 8).cuda() * 0.7
+        real = synth.shots(batch, 32, 9).cuda()
+        want_f, want_r = D(fake)[0], D(real)[0]
+        got_f, got_r = d_pair(D, fake, real)
+        assert got_f.shape == want_f.shape and got_r.shape == want_r.shape
+        torch.testing.assert_close(got_f, want_f, rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(got_r, want_r, rtol=1e-4, atol=1e-5)
+        # a wrong grouping shows up immediately: scoring the plain concatenation mixes the two batches' statistics
+        if batch == 2:
+            mixed = D(torch.cat([fake, real]))[0]
+            assert not torch.allclose(mixed[:batch], want_f, rtol=1e-4, atol=1e-5)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
