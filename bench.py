@@ -366,6 +366,15 @@ def op_sweep(device):
     ms = _time_kernel(lambda: op.upfirdn2d(ya, k12, down=2), flush, iters=5)
     out["aug_sym6_down2_553"] = 4 * (ya.numel() + ya.numel() // 4) / ms / 1e6
     del xa, ya
+    # fused masks + Adam + EMA over 33.5 M parameters (G + D trainables are 59 M): 36 B per parameter
+    from rick_b200.optim import FusedMaskedAdam
+    pw = torch.nn.Parameter(torch.randn(64, 512, 1024, device=device))
+    pe = torch.nn.Parameter(pw.detach().clone())
+    pw.grad = torch.randn_like(pw)
+    fopt = FusedMaskedAdam({"w": pw}, [pw], lr=2e-3, betas=(0.0, 0.99), ema_named={"w": pe}, ema_decay=0.998)
+    ms = _time_kernel(lambda: fopt.step(ema=True), flush, iters=5)
+    out["adam_mask_ema_33M"] = 36 * pw.numel() / ms / 1e6
+    del pw, pe, fopt
     from rick_b200 import conv_tc as ct
     xn = torch.randn(n, 129, 129, c, device=device)                       # NHWC blur after the transposed conv
     ms = _time_kernel(lambda: ct.blur_nhwc(xn, taps4, (1, 1)), flush, iters=5)

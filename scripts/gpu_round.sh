@@ -28,12 +28,12 @@ ncu)
       > gpurun_out/ncu_bench${NCU_TAG}.log 2>&1
   echo "ncu launches rc=$?"
   timeout 300 ncu --set full --clock-control none --import-source on \
-      -k regex:'upfirdn2d|bias_act_vec|bias_act_bwd|blur_nhwc|conv_tc' -s 8 -c 8 \
+      -k regex:'upfirdn2d|bias_act_vec|bias_act_bwd|blur_nhwc|conv_tc|adam_mask_ema' -s 9 -c 9 \
       -o gpurun_out/prof_ops python -u scripts/prof_ops.py > gpurun_out/ncu_ops.log 2>&1
   echo "ncu ops rc=$?" ;;
 ncuops)
   timeout 300 ncu --set full --clock-control none --import-source on \
-      -k regex:'upfirdn2d|bias_act_vec|bias_act_bwd|blur_nhwc|conv_tc' -s 8 -c 8 \
+      -k regex:'upfirdn2d|bias_act_vec|bias_act_bwd|blur_nhwc|conv_tc|adam_mask_ema' -s 9 -c 9 \
       -o gpurun_out/prof_ops python -u scripts/prof_ops.py > gpurun_out/ncu_ops.log 2>&1
   echo "ncu ops rc=$?" ;;
 esac

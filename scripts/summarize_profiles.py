@@ -14,7 +14,8 @@ OUT = os.path.join(ROOT, "gpurun_out")
 PROF = os.path.join(ROOT, "profiles")
 
 OURS = ("rick::", "upfirdn2d", "bias_act", "bias_grad", "fisher_multi", "filter_fim", "percentile_kernel", "decide_kernel",
-        "mask_apply", "conv_tc", "blur_nhwc", "to_rgb_nhwc")
+        "mask_apply", "conv_tc", "blur_nhwc", "to_rgb_nhwc", "adam_mask_ema", "colsum_bwd", "modulate_kernel",
+        "styled_epilogue")
 
 
 def short(name):
