@@ -261,7 +261,7 @@ def run_ours(args):
             line["extra"]["g_samples_per_s_b64_whole_job"] = float(t.item())
         rdist.barrier()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         # Tearing down a NCCL process group while CUDA graphs that recorded its collectives are still alive can block
         # (observed in round 1: the JSON line was out, the process never exited).  Everything is flushed: leave hard.
@@ -270,6 +270,15 @@ def run_ours(args):
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
+
+
+_JSON_OUT = None
+
+
+def emit(line: dict):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def _traffic(kernel):
@@ -512,7 +521,7 @@ def run_reference(args):
                              "sample": f"{k_run} plain adaptation iterations, 256 px, batch 2, {cores} threads"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -529,6 +538,12 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    # stdout carries exactly ONE line, the JSON: anything a library writes to file descriptor 1 on the way (NCCL's
+    # version banner, cuDNN notes) is sent to stderr instead; the JSON line goes out through the saved descriptor
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
