@@ -150,6 +150,12 @@ RICK_API int rick_adam_mask_ema(float* const* param, const float* const* grad, f
                        int count, float lr, float beta1, float beta2, float eps, float ema_decay,
                        rick_stream_t stream);
 
+/* out[t] = in[t] * scale[t] over count dense float32 tensors in one launch: the equalised-lr multipliers of EqualConv2d /
+ * EqualLinear (model_probe_tune.py:124, 160-164: ``self.weight * self.scale``, ``self.bias * self.lr_mul``) for a whole
+ * network pass, and their backward (grad * scale).  Tables are HOST arrays. */
+RICK_API int rick_scale_multi(float* const* out, const float* const* in, const float* scale, const int64_t* numel, int count,
+                     rick_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------- tcgen05 convolution
  * Implicit-GEMM convolution on NHWC fp32 activations (TF32 tensor-core math, fp32 accumulate), replacing the grouped
  * cuDNN convolutions of ModulatedConv2d (gan_training/models/model_probe_tune.py:265, 274, 280) and the dense ones

@@ -155,6 +155,12 @@ class RickAdapter:
         self.g_train = [p for n, p in self.g_named.items() if "convs" in n]
         self.d_train = [p for n, p in self.d_named.items()
                         if ("convs" in n and "convs.0" not in n) or "final" in n]
+        if self.device.type == "cuda":
+            from . import stylegan2 as _sg
+            _sg.declare_prescale_groups(generator, self.g_train)          # trainable subset | rest
+            _sg.declare_prescale_groups(discriminator, self.d_train)
+            _sg.declare_prescale_groups(g_ema, list(g_ema.parameters()))    # the Fisher round differentiates all of them
+            _sg.declare_prescale_groups(d_ema, list(d_ema.parameters()))
         self.acc_g = rick.FisherAccumulator(g_ema.named_parameters())
         self.acc_d = rick.FisherAccumulator(d_ema.named_parameters())
         self.masks_g = rick.FilterMasks(rick.generator_layers(dict(g_ema.named_parameters())), self.device)

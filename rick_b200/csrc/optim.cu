@@ -120,8 +120,71 @@ __global__ void __launch_bounds__(256) adam_mask_ema_kernel(const __grid_constan
     }
 }
 
+// ---- out[t] = in[t] * scale[t] for a whole network's weights in one launch --------------------------------------
+// The equalised-lr multipliers (EqualConv2d / EqualLinear: weight * 1/sqrt(fan_in), bias * lr_mul,
+// model_probe_tune.py:110-124, 155-165) are ~45 separate 2-microsecond element-wise launches per network pass and as
+// many again in backward; as a multi-tensor kernel they are one launch each way.
+constexpr int kMaxScaleTensors = 160;
+constexpr int kScaleChunk = 256 * 16;
+struct ScaleTable {
+    float* out[kMaxScaleTensors];
+    const float* in[kMaxScaleTensors];
+    long long numel[kMaxScaleTensors];
+    float scale[kMaxScaleTensors];
+    int block_end[kMaxScaleTensors];
+    int count;
+};
+
+__global__ void __launch_bounds__(256) scale_multi_kernel(const __grid_constant__ ScaleTable tab) {
+    int t = 0;
+    while (t < tab.count - 1 && (int)blockIdx.x >= tab.block_end[t]) ++t;
+    const int local_block = blockIdx.x - (t ? tab.block_end[t - 1] : 0);
+    float* __restrict__ out = tab.out[t];
+    const float* __restrict__ in = tab.in[t];
+    const float s = tab.scale[t];
+    const long long n = tab.numel[t];
+    const long long begin = (long long)local_block * kScaleChunk;
+    const long long end = min(begin + (long long)kScaleChunk, n);
+    if (((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(in)) & 15) == 0 && (n & 3) == 0) {
+        for (long long i = begin + threadIdx.x * 4; i < end; i += 256 * 4) {
+            float4 v = *reinterpret_cast<const float4*>(in + i);
+            v.x *= s, v.y *= s, v.z *= s, v.w *= s;
+            *reinterpret_cast<float4*>(out + i) = v;
+        }
+    } else {
+        for (long long i = begin + threadIdx.x; i < end; i += 256) out[i] = in[i] * s;
+    }
+}
+
 }  // namespace
 }  // namespace rick
+
+extern "C" int rick_scale_multi(float* const* out, const float* const* in, const float* scale, const int64_t* numel,
+                                int count, rick_stream_t stream) {
+    using namespace rick;
+    if (!out || !in || !scale || !numel || count < 0) return RICK_ERR_INVALID_ARGUMENT;
+    for (int base = 0; base < count; base += kMaxScaleTensors) {
+        ScaleTable tab{};
+        const int n = (count - base < kMaxScaleTensors) ? count - base : kMaxScaleTensors;
+        long long blocks = 0;
+        int used = 0;
+        for (int i = 0; i < n; ++i) {
+            const int k = base + i;
+            if (numel[k] < 0 || !out[k] || !in[k]) return RICK_ERR_INVALID_ARGUMENT;
+            if (numel[k] == 0) continue;
+            tab.out[used] = out[k], tab.in[used] = in[k], tab.numel[used] = numel[k], tab.scale[used] = scale[k];
+            blocks += ceil_div(numel[k], kScaleChunk);
+            if (blocks > 0x7fffffffLL) return RICK_ERR_OVERFLOW;
+            tab.block_end[used] = (int)blocks;
+            ++used;
+        }
+        if (!used) continue;
+        tab.count = used;
+        scale_multi_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(tab);
+        RICK_CHECK_LAUNCH();
+    }
+    return RICK_OK;
+}
 
 extern "C" int rick_adam_mask_ema(float* const* param, const float* const* grad, float* const* exp_avg,
                                   float* const* exp_avg_sq, float* const* ema, const uint8_t* const* state,

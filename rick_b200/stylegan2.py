@@ -28,6 +28,7 @@ from torch.nn import functional as F
 
 from . import conv as _conv
 from .op import FusedLeakyReLU, fused_leaky_relu, upfirdn2d
+from .op.scale import scale_all
 
 
 # Activation memory format inside G / D.  Channels-last keeps the library convolutions in their native NHWC kernels
@@ -36,6 +37,7 @@ from .op import FusedLeakyReLU, fused_leaky_relu, upfirdn2d
 _CHANNELS_LAST = os.environ.get("RICK_CHANNELS_LAST", "1") != "0"
 
 
+_PRESCALE = os.environ.get("RICK_PRESCALE", "1") != "0"           # one multi-tensor launch for all equalised-lr multipliers
 _FUSED_STYLED = os.environ.get("RICK_FUSED_STYLED", "1") != "0"   # fused modulate / demod-noise-bias-act ops in StyledConv
 
 
@@ -117,6 +119,56 @@ class Blur(nn.Module):
         return upfirdn2d(input, self.kernel, pad=self.pad)
 
 
+def declare_prescale_groups(net: nn.Module, *param_groups):
+    """Turn on one-launch equalised-lr scaling for ``net`` (rick_b200.op.scale.scale_all).  Each group of parameters is
+    scaled by its own autograd node, so a backward restricted to one group (``autograd.backward(loss, inputs=group)``,
+    as the adaptation loop does for the trainable subset) still skips every gradient of the others -- with a single
+    node autograd would have to produce ALL weight gradients (e.g. the K = 65536 weight gradient of each ToRGB) before
+    it could run.  Parameters in no group form a last group of their own."""
+    plan = []
+    for m in net.modules():
+        if isinstance(m, EqualConv2d):
+            plan.append((m, "_ws", m.weight, m.scale))
+        elif isinstance(m, EqualLinear):
+            plan.append((m, "_ws", m.weight, m.scale))
+            if m.bias is not None:
+                plan.append((m, "_bs", m.bias, m.lr_mul))
+    groups, taken = [], set()
+    for params in param_groups:
+        ids = {id(p) for p in params}
+        grp = [e for e in plan if id(e[2]) in ids and id(e[2]) not in taken]
+        taken |= {id(e[2]) for e in grp}
+        if grp:
+            groups.append(grp)
+    rest = [e for e in plan if id(e[2]) not in taken]
+    if rest:
+        groups.append(rest)
+    object.__setattr__(net, "_prescale_groups", groups)
+
+
+class _Prescaled:
+    """``with _Prescaled(net):`` -- every EqualConv2d / EqualLinear of ``net`` finds its equalised-lr-scaled weight
+    (and bias) ready for the pass: one multi-tensor launch per declared group instead of one element-wise launch per
+    module, forward and backward.  Same values, same gradients.  A no-op until declare_prescale_groups(net, ...)."""
+
+    def __init__(self, net: nn.Module):
+        self.groups = getattr(net, "_prescale_groups", None) if _PRESCALE else None
+
+    def __enter__(self):
+        if self.groups and self.groups[0][0][2].is_cuda:
+            for grp in self.groups:
+                outs = scale_all([p for _, _, p, _ in grp], [s for *_, s in grp])
+                for (m, slot, _, _), o in zip(grp, outs):
+                    setattr(m, slot, o)
+        return self
+
+    def __exit__(self, *exc):
+        for grp in self.groups or ():
+            for m, slot, _, _ in grp:
+                setattr(m, slot, None)
+        return False
+
+
 class EqualConv2d(nn.Module):
     def __init__(self, in_channel, out_channel, kernel_size, stride=1, padding=0, bias=True):
         super().__init__()
@@ -126,8 +178,11 @@ class EqualConv2d(nn.Module):
         self.padding = padding
         self.bias = nn.Parameter(torch.zeros(out_channel)) if bias else None
 
+    _ws = None                                             # scaled weight handed in by _Prescaled for one pass
+
     def forward(self, input):
-        return _conv.conv2d(input, self.weight * self.scale, self.bias, stride=self.stride, padding=self.padding)
+        w = self._ws if self._ws is not None else self.weight * self.scale
+        return _conv.conv2d(input, w, self.bias, stride=self.stride, padding=self.padding)
 
     def __repr__(self):
         o, i, k, _ = self.weight.shape
@@ -143,10 +198,15 @@ class EqualLinear(nn.Module):
         self.scale = (1 / math.sqrt(in_dim)) * lr_mul
         self.lr_mul = lr_mul
 
+    _ws = None                                             # scaled weight / bias handed in by _Prescaled
+    _bs = None
+
     def forward(self, input):
+        w = self._ws if self._ws is not None else self.weight * self.scale
+        b = self._bs if self._bs is not None else (self.bias * self.lr_mul if self.bias is not None else None)
         if self.activation:
-            return fused_leaky_relu(F.linear(input, self.weight * self.scale), self.bias * self.lr_mul)
-        return F.linear(input, self.weight * self.scale, bias=self.bias * self.lr_mul)
+            return fused_leaky_relu(F.linear(input, w), b)
+        return F.linear(input, w, bias=b)
 
     def __repr__(self):
         return f"{self.__class__.__name__}({self.weight.shape[1]}, {self.weight.shape[0]})"
@@ -313,8 +373,12 @@ class Generator(nn.Module):
     def estimate_fisher(self, loglikelihood):
         return _estimate_fisher(self, loglikelihood)
 
-    def forward(self, styles, return_latents=False, inject_index=None, truncation=1, truncation_latent=None,
-                input_is_latent=False, noise=None, randomize_noise=True, return_feats=False):
+    def forward(self, *args, **kwargs):
+        with _Prescaled(self):
+            return self._forward(*args, **kwargs)
+
+    def _forward(self, styles, return_latents=False, inject_index=None, truncation=1, truncation_latent=None,
+                 input_is_latent=False, noise=None, randomize_noise=True, return_feats=False):
         if not input_is_latent:
             styles = [self.style(s) for s in styles]
         if noise is None:
@@ -408,7 +472,11 @@ class Discriminator(nn.Module):
     def estimate_fisher(self, loglikelihood):
         return _estimate_fisher(self, loglikelihood)
 
-    def forward(self, inp, ind=None, real=False, stddev_group=None):
+    def forward(self, *args, **kwargs):
+        with _Prescaled(self):
+            return self._forward(*args, **kwargs)
+
+    def _forward(self, inp, ind=None, real=False, stddev_group=None):
         """``stddev_group``: override of ``min(batch, self.stddev_group)`` for the minibatch-stddev grouping -- used by
         rick_b200.adapt.d_pair to score two batches in one pass with each batch's own statistics."""
         feat: list = []

@@ -323,3 +323,30 @@ def test_fused_modulate_and_styled_epilogue(shape):
     grads = torch.autograd.grad(y, leaves, go.cuda())
     for a_, b_ in zip(grads, wg):
         _close(a_, b_, 2e-4)
+
+
+def test_scale_all_matches_per_tensor_multiplies():
+    """rick_scale_multi (all equalised-lr multipliers of a network in one launch): values, gradients, second-order."""
+    from rick_b200.op.scale import scale_all
+    g = torch.Generator().manual_seed(11)
+    shapes = [(512, 512), (512,), (128, 64, 3, 3), (7, 5), (1, 513)]
+    scales = [0.0442, 0.01, 1 / 24.0, 3.0, 1.0]
+    ts = [torch.randn(s, generator=g).cuda().requires_grad_(True) for s in shapes]
+    ts[2] = ts[2].detach().to(memory_format=torch.channels_last).requires_grad_(True)
+    outs = scale_all(ts, scales)
+    for o, t, s in zip(outs, ts, scales):
+        assert o.stride() == t.stride()
+        torch.testing.assert_close(o, t.detach() * s, rtol=0, atol=0)
+    go = [torch.randn(s, generator=g).cuda() for s in shapes]
+    grads = torch.autograd.grad(outs, ts, go)
+    for gr, gg, s in zip(grads, go, scales):
+        torch.testing.assert_close(gr, gg * s, rtol=0, atol=0)
+    # second order through a nonlinearity on the outputs
+    outs = scale_all(ts, scales)
+    loss = sum((o ** 3).sum() for o in outs)
+    g1 = torch.autograd.grad(loss, ts, create_graph=True)
+    g2 = torch.autograd.grad(sum((a ** 2).sum() for a in g1), ts)
+    for t, s, h in zip(ts, scales, g2):
+        x = t.detach().double()
+        want = 2 * (3 * s ** 3 * x ** 2) * (6 * s ** 3 * x)       # d/dx (3 s^3 x^2)^2
+        torch.testing.assert_close(h.double(), want, rtol=1e-4, atol=1e-6)
