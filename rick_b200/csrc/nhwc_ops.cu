@@ -324,6 +324,62 @@ __global__ void __launch_bounds__(256) to_rgb_nhwc_kernel(float* __restrict__ rg
     }
 }
 
+// Four pixels per warp pass.  The single-pixel kernel above spends 15 shuffles + 15 adds per pixel on its three
+// warp-wide sums -- more issue slots than a 512-byte pixel (C = 128) can pay for at HBM speed (0.32 of the copy rate in the
+// round-1 profile).  Here a lane accumulates 4 pixels x 3 colours = 12 partial sums (16 slots) and the warp reduces all
+// of them with ONE transposing butterfly: every exchange halves the slots a lane still carries (8 + 4 + 2 + 1 + 1 = 16
+// shuffles for four pixels instead of 60), and 4 independent 16-byte loads per lane are in flight per channel group.
+__global__ void __launch_bounds__(256) to_rgb_nhwc_kernel4(float* __restrict__ rgb, const float* __restrict__ y,
+                                                           const float* __restrict__ wmod,
+                                                           const float* __restrict__ bias,
+                                                           const float* __restrict__ skip, int batch, int hw, int c4) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long quads = (long long)batch * hw / 4;            // hw % 4 == 0: the 4 pixels share their sample
+    for (long long qd = warp0; qd < quads; qd += nwarps) {
+        const long long pix = qd * 4;
+        const int b = (int)(pix / hw);
+        const int q = (int)(pix - (long long)b * hw);
+        const float4* a = reinterpret_cast<const float4*>(y) + pix * c4;
+        const float4* w0 = reinterpret_cast<const float4*>(wmod) + (long long)b * 3 * c4;
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+        for (int i = lane; i < c4; i += 32) {
+            float4 x[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) x[p] = ld_stream_f4(a + (long long)p * c4 + i);
+            const float4 u0 = __ldg(w0 + i), u1 = __ldg(w0 + c4 + i), u2 = __ldg(w0 + 2 * c4 + i);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                v[p * 4 + 0] += x[p].x * u0.x + x[p].y * u0.y + x[p].z * u0.z + x[p].w * u0.w;
+                v[p * 4 + 1] += x[p].x * u1.x + x[p].y * u1.y + x[p].z * u1.z + x[p].w * u1.w;
+                v[p * 4 + 2] += x[p].x * u2.x + x[p].y * u2.y + x[p].z * u2.z + x[p].w * u2.w;
+            }
+        }
+        // transposing butterfly: after the exchange over lane bit k a lane keeps half of its slots
+#pragma unroll
+        for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+            const bool upper = (lane & bit) != 0;
+#pragma unroll
+            for (int j = 0; j < half; ++j) {
+                const float send = upper ? v[j] : v[j + half];
+                const float keep = upper ? v[j + half] : v[j];
+                v[j] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+            }
+        }
+        float r = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+        const int slot = lane >> 1, p = slot >> 2, k = slot & 3;      // slot = 4 * pixel + colour
+        if ((lane & 1) == 0 && k < 3) {
+            const long long o = ((long long)b * 3 + k) * hw + q + p;     // NCHW image
+            r += __ldg(bias + k);
+            if (skip) r += __ldg(skip + o);
+            rgb[o] = r;
+        }
+    }
+}
+
 }  // namespace
 }  // namespace rick
 
@@ -412,8 +468,15 @@ extern "C" int rick_to_rgb_nhwc(float* rgb, const float* y, const float* wmod, c
     long long blocks = ceil_div(pixels, 8);
     const long long cap = (long long)kNumSMs * 16;
     if (blocks > cap) blocks = cap;
-    to_rgb_nhwc_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(rgb, y, wmod, bias, skip, batch,
-                                                                                         h * w, channels / 4);
+    if ((h * w) % 4 == 0) {
+        blocks = ceil_div(pixels / 4, 8);
+        if (blocks > cap) blocks = cap;
+        to_rgb_nhwc_kernel4<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(rgb, y, wmod, bias, skip,
+                                                                                              batch, h * w, channels / 4);
+    } else {
+        to_rgb_nhwc_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(rgb, y, wmod, bias, skip,
+                                                                                             batch, h * w, channels / 4);
+    }
     RICK_CHECK_LAUNCH();
     return RICK_OK;
 }

@@ -130,11 +130,12 @@ def test_blur_nhwc_fused_epilogue():
     assert _err(plain.permute(0, 3, 1, 2), ops.upfirdn2d(x.cpu(), taps.cpu(), pad=(2, 2)).cuda()) < 1e-5
 
 
-def test_to_rgb_nhwc():
+@pytest.mark.parametrize("b,c,h,w", [(2, 128, 16, 16), (3, 512, 4, 4), (2, 64, 8, 6), (1, 36, 5, 3), (2, 256, 33, 1)])
+def test_to_rgb_nhwc(b, c, h, w):
+    """4-pixel butterfly kernel (H*W % 4 == 0) and the one-pixel kernel (odd pixel counts), ragged channel counts."""
     from rick_b200 import conv_tc as ct
-    b, c, h = 2, 128, 16
-    y, wmod, bias, skip = _rand(b, h, h, c, seed=30), _rand(b, 3, c, seed=31), _rand(3, seed=32), _rand(b, 3, h, h, seed=33)
-    want = torch.einsum("bhwc,boc->bohw", y, wmod) + bias[None, :, None, None]
+    y, wmod, bias, skip = _rand(b, h, w, c, seed=30), _rand(b, 3, c, seed=31), _rand(3, seed=32), _rand(b, 3, h, w, seed=33)
+    want = torch.einsum("bhwc,boc->bohw", y.double(), wmod.double()).float() + bias[None, :, None, None]
     assert _err(ct.to_rgb_nhwc(y, wmod, bias, None), want) < 1e-5
     assert _err(ct.to_rgb_nhwc(y, wmod, bias, skip), want + skip) < 1e-5
 
