@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(256) upfirdn2d_tiled(UpfirdnParams p) {
 // instruction issue / occupancy, 63 % issue active, DRAM 53 %).  CTA = 32 x 8 threads = 128 x (8*OY) outputs.
 template <typename T, int UP, int DOWN, int PX, int PY, int OY>
 __global__ void __launch_bounds__(256) upfirdn2d_direct(UpfirdnParams p) {
-    constexpr int OX = 4;
+    constexpr int OX = 16 / (int)sizeof(T);     // 16 bytes of outputs per thread and row: 4 fp32 / 8 bf16
     using WX = Window<UP, DOWN, PX, OX>;
     using WY = Window<UP, DOWN, PY, OY>;
     constexpr int WW = WX::size, WH = WY::size;
@@ -318,8 +318,8 @@ __global__ void __launch_bounds__(256) upfirdn2d_direct(UpfirdnParams p) {
     }
 
     T* out = static_cast<T*>(p.out) + (plane * p.out_h + oy0) * (long long)p.out_w + ox0;
-    // 4 outputs leave as one 16-byte (fp32) / 8-byte (bf16) store; the caller guarantees a 16-byte aligned base
-    const bool vec_ok = (ox0 + OX <= p.out_w) && ((p.out_w & 3) == 0);
+    // OX outputs leave as one 16-byte store; the caller guarantees a 16-byte aligned base
+    const bool vec_ok = (ox0 + OX <= p.out_w) && ((p.out_w & (OX - 1)) == 0);
     const bool fast = vec_ok && (oy0 + OY <= p.out_h);
 #pragma unroll
     for (int oy = 0; oy < OY; ++oy) {
@@ -345,13 +345,16 @@ __global__ void __launch_bounds__(256) upfirdn2d_direct(UpfirdnParams p) {
         }
         T* row = out + (long long)oy * p.out_w;
         if (vec_ok) {
-            if (sizeof(T) == 4) {
+            if constexpr (sizeof(T) == 4) {
                 st_stream_f4(reinterpret_cast<float4*>(row), make_float4(acc[0], acc[1], acc[2], acc[3]));
             } else {
-                const __nv_bfloat162 lo = __floats2bfloat162_rn(acc[0], acc[1]), hi = __floats2bfloat162_rn(acc[2], acc[3]);
-                uint2 pk;
-                pk.x = *reinterpret_cast<const unsigned*>(&lo), pk.y = *reinterpret_cast<const unsigned*>(&hi);
-                *reinterpret_cast<uint2*>(row) = pk;
+                float4 pk;                                   // 8 bf16 = 16 bytes
+                __nv_bfloat162 h2;
+                h2 = __floats2bfloat162_rn(acc[0], acc[1]), pk.x = *reinterpret_cast<const float*>(&h2);
+                h2 = __floats2bfloat162_rn(acc[2], acc[3]), pk.y = *reinterpret_cast<const float*>(&h2);
+                h2 = __floats2bfloat162_rn(acc[4], acc[5]), pk.z = *reinterpret_cast<const float*>(&h2);
+                h2 = __floats2bfloat162_rn(acc[6], acc[7]), pk.w = *reinterpret_cast<const float*>(&h2);
+                st_stream_f4(reinterpret_cast<float4*>(row), pk);
             }
         } else {
 #pragma unroll
@@ -588,7 +591,7 @@ static int launch_rows(UpfirdnParams p, cudaStream_t stream) {
 
 template <typename T, int UP, int DOWN, int PX, int PY, int OY>
 static int launch_direct(UpfirdnParams p, cudaStream_t stream) {
-    p.tiles_x = (int)ceil_div(p.out_w, 128);
+    p.tiles_x = (int)ceil_div(p.out_w, 32 * (16 / (int)sizeof(T)));
     p.tiles_y = (int)ceil_div(p.out_h, 8 * OY);
     const long long blocks = (long long)p.tiles_x * p.tiles_y * p.planes;
     if (blocks > 0x7fffffffLL) return RICK_ERR_OVERFLOW;

@@ -350,3 +350,18 @@ def test_scale_all_matches_per_tensor_multiplies():
         x = t.detach().double()
         want = 2 * (3 * s ** 3 * x ** 2) * (6 * s ** 3 * x)       # d/dx (3 s^3 x^2)^2
         torch.testing.assert_close(h.double(), want, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("shape,pad", [((2, 3, 64, 64), (2, 1)), ((1, 2, 70, 50), (2, 1)), ((1, 2, 40, 68), (1, 2)),
+                                       ((1, 1, 33, 36), (3, 0))])
+def test_upfirdn2d_up2_bf16_large(shape, pad):
+    """bf16 storage on the large-map up = 2 kernel (8 outputs = one 16-byte store per thread and row), incl. widths that
+    are not a multiple of 8 (scalar tail) and odd pad phases."""
+    from rick_b200 import op
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(shape, generator=g).to(torch.bfloat16)
+    taps = torch.randn(4, 4, generator=g)
+    want = ops.upfirdn2d(x.float(), taps, 2, 1, pad)
+    got = op.upfirdn2d(x.cuda(), taps.cuda(), 2, 1, pad)
+    assert got.dtype == torch.bfloat16 and tuple(got.shape) == tuple(want.shape)
+    _close(got.float(), want, 1e-2)
