@@ -15,8 +15,11 @@ line says how many Fisher / R1 / path-length iterations were inside the timed re
           memory and reads the step's losses back to the host
   N > 1   one process per GPU (torchrun), DDP-style gradient all-reduce over NCCL, per-GPU batch 2 (weak scaling);
           value = N x (iterations/s), i.e. batch-2 iteration equivalents per second over the whole job
-  roofline  the package's memory-bound headline kernel (upfirdn2d, BASELINE configs[3] shape (32,512,128,128)->256^2)
-            timed with CUDA events on the launching stream, L2 flushed between launches, against MEASURED_PEAKS.json
+  roofline  the tcgen05 modulated convolution (conv_tc_kernel, 64x64 512->512 layer at the sample-generation batch):
+            TF32 flops / launch time against bf16_tflops / 2 of MEASURED_PEAKS.json; ``rooflines`` adds the memory-bound
+            headline kernel (upfirdn2d, BASELINE configs[3] shape (32,512,128,128)->256^2) against hbm_gbs.  Both are
+            timed with CUDA events on the launching stream, L2 flushed between launches; extra.op_sweep holds the rest
+            of configs[3] (blur / down / bias-act / optimiser step, fp32 and bf16)
   cpu_baseline / --impl reference   the oracle port of the same iteration on the box's host cores (the reference's
           CPU path: upfirdn2d_native + native leaky-ReLU semantics), bounded sample
 """

@@ -7,18 +7,18 @@
 //   U = zero-stuffed (factor up), then padded (negative pad = crop) input;  U[Y, X] = in[(Y-pad_y0)/up, (X-pad_x0)/up]
 //   when both divisions are exact and in range, else 0.
 //
-// Two kernels:
-//   upfirdn2d_tiled   minor == 1 (NCHW planes), 4x4 taps, (up, down) in {(1,1), (2,1), (1,2)} -- every shape the
-//                     StyleGAN2 G/D stack issues.  A CTA stages an input halo tile (several planes for small
-//                     feature maps) in shared memory with coalesced loads and implicit zero padding; each thread
-//                     then owns a 4-wide x OY-tall patch of outputs, pulls its input window from shared memory with
-//                     128/64-bit loads and keeps taps + window in registers.  The polyphase structure (which taps
-//                     hit real samples) is resolved at compile time from (UP, pad mod UP), so up=2 does 4 FMAs per
-//                     output, not 16.  Outputs leave as 128-bit stores.  HBM-bound: 4 B read per input + 4 B
-//                     written per output sample (fp32).
-//   upfirdn2d_generic any taps / factors / minor: one thread per output sample, gathers valid taps from global
-//                     memory (L1/L2 provide the reuse).  Correctness path for the shapes the model never issues
-//                     (e.g. the 12x12 taps of non_leaking.py).
+// Kernels (all minor == 1, i.e. NCHW planes, except the last):
+//   upfirdn2d_direct  4x4 taps, large maps, up = 2: a thread owns an OY x (16 bytes of) output patch, pulls its input
+//                     window straight from global memory (L1 shares it between neighbours), FIR in registers with the
+//                     polyphase structure resolved at compile time (4 FMAs per output, not 16), 128-bit stores.
+//   upfirdn2d_rows    4x4 taps, large maps, up = 1 (blur, down = 2): one cp.async.bulk per CTA stages TR full-width
+//                     input rows; lane = output column sliding down the rows, packed FFMA2, no predicates in the loop.
+//   upfirdn2d_tiled   4x4 taps, small maps: a CTA stages an input halo tile (several planes for tiny feature maps) in
+//                     shared memory with coalesced loads and implicit zero padding; 4 x OY outputs per thread.
+//   upfirdn2d_generic any taps / factors / minor: one thread per output sample, taps staged in shared memory, only
+//                     the taps that land on real samples are visited (the 12x12 taps of non_leaking.py).
+// All are HBM-bound by design: 4 B read per input + 4 B written per output sample (fp32); what limited the earlier
+// versions was instruction issue, see the notes at each kernel.
 #include <algorithm>
 #include <type_traits>
 
@@ -371,11 +371,16 @@ __global__ void __launch_bounds__(256) upfirdn2d_direct(UpfirdnParams p) {
 // strided, mis-aligned window loads (odd widths 2^k + 1 are the common case: the blur after a transposed conv reads
 // 129 -> 128, D's blur writes 128 -> 129).  Here a CTA owns TR full-width output rows of one plane: the input rows
 // they need are ONE contiguous span of the NCHW tensor, fetched with a single cp.async.bulk (aligned down/up to
-// 16 B; rows outside the image are simply not fetched and read as zero).  Several CTAs are resident per SM, so
+// 16 B; rows outside the image are not fetched, the CTA zero-fills them).  Several CTAs are resident per SM, so
 // their bulk copies overlap the FIR of the others without holding registers.  Compute: lane = output column, a warp
-// slides down SR rows keeping the 4x4 window in registers (4 conflict-free LDS + 16 FMA per output for down = 1), and
-// every warp-wide store is 128 contiguous bytes.  The <= 4 columns left over when out_w = 32 k + r are done
-// transposed (lane = row), so 129-wide planes do not pay for a fifth, almost empty column group.
+// slides down its rows keeping the 4x4 window in registers (4 conflict-free LDS + 8 FFMA2 per output for down = 1),
+// and every warp-wide store is 128 contiguous bytes.  The <= 4 columns left over when out_w = 32 k + r are reduced
+// with shuffles (see "edge columns"), so 129-wide planes do not pay for a fifth, almost empty column group.
+//
+// The kernel is bound by instruction issue, not by bandwidth; what took it from 0.55 to 1.0 of the HBM copy rate
+// (blur 129 -> 128, ncu: 70 % issue-slot utilisation, "not selected" the top stall) was removing instructions per
+// output: column masks folded into the taps (no predicates), FFMA2, and ONE long item per warp in 4-warp CTAs so the
+// per-CTA / per-item set-up (~250 + ~100 instructions per warp) is amortised over 48-64 rows.
 template <typename T> __device__ __forceinline__ float smem_val(const T* p);
 template <> __device__ __forceinline__ float smem_val<float>(const float* p) { return *p; }
 template <> __device__ __forceinline__ float smem_val<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }

@@ -1,20 +1,24 @@
 """CUDA-graph execution of the adaptation iteration.
 
-At batch 2 the iteration is launch-bound: a few thousand small kernels per step, each costing more host time than
-device time.  ``GraphedRickAdapter`` records the four sub-steps of ``RickAdapter.step`` -- D step, R1, G step,
-path-length -- once (forward, backward, mask application, fused Adam, and for the D step the weight re-pack + tcgen05
-generator forward) and replays them; EMA rides at the end of the G-step graph.  Everything data dependent is a device
-buffer written before the replay:
+At batch 2 the iteration is launch-bound: about two thousand small kernels per step, each costing more host time than
+device time.  ``GraphedRickAdapter`` records the sub-steps of ``RickAdapter.step`` -- D step (one joint pass over fake +
+real), R1, G step, path-length, EMA -- once (forward, backward, the fused masks + Adam launch, and for the D step the
+weight re-pack + tcgen05 generator forward) and replays them.  Everything data dependent is a device buffer written
+before the replay:
 
     real images        static (B, 3, S, S) buffer, filled by ``copy_`` from the caller's tensor
     style mixing       z1, z2 are always drawn (device RNG inside the graph); the crossover index is a device scalar,
                        ``n_latent`` meaning "no mixing" -- latent = where(layer < index, w1, w2), which equals the
                        reference's concat of repeats (model_probe_tune.py:544-560)
     masks              the byte masks are device resident and updated in place by the Fisher round
+    Adam step counts   per-parameter device floats (rick_b200.optim.FusedMaskedAdam)
 
-The Fisher round itself (once per ``fisher_freq`` iterations) stays eager.  Under torchrun (world_size > 1) the
-DDP gradient all-reduce is captured inside the graphs (NCCL supports stream capture), so every rank replays the same
-sequence of collectives.
+The Fisher round (once per ``fisher_freq`` iterations) replays a sixth graph -- its per-image body: G forward, joint D
+pass, two backward passes, grad**2 accumulation -- and keeps the exchange step, the percentile and the mask update eager
+(164 -> 50 ms per round at 256 px).  Capturing a graph runs its body twice as warm-up; for the training sub-steps those
+are real optimiser steps, for the Fisher body the accumulators are cleared afterwards.  Under torchrun (world_size > 1)
+the DDP gradient all-reduce is captured inside the graphs (NCCL supports stream capture), so every rank replays the
+same sequence of collectives.
 """
 from __future__ import annotations
 

@@ -327,3 +327,34 @@ def test_lib_conv_first_and_second_order_match_autograd(transposed, stride, padd
         res.append((y.detach(), gx.detach(), gw.detach(), ggx, ggw, gw_from_gx))
     for a, b in zip(*res):
         torch.testing.assert_close(a, b, rtol=1e-10, atol=1e-10)
+
+
+# ------------------------------------------------------------------------------------------ joint D pass
+@pytest.mark.parametrize("batch,cap", [(2, 25), (6, 4), (8, 4), (50, 25), (3, 4)])
+def test_d_pair_grouping_matches_two_calls(batch, cap):
+    """adapt.d_pair stacks fake and real so that every minibatch-stddev group of the joint call is a group of ONE of the
+    two batches -- checked on a stand-in discriminator that has nothing but that statistic (model_probe_tune.py:749-756)."""
+    from rick_b200.adapt import d_pair
+
+    class StddevOnly(torch.nn.Module):
+        stddev_group = cap
+
+        def forward(self, x, stddev_group=None):
+            b = x.shape[0]
+            group = min(b, self.stddev_group) if stddev_group is None else stddev_group
+            sd = x.view(group, -1, *x.shape[1:])
+            sd = torch.sqrt(sd.var(0, unbiased=False) + 1e-8).mean(dim=(1, 2, 3), keepdim=True)   # one value per group
+            sd = sd.repeat(group, 1, 1, 1)
+            return (x.mean(dim=(1, 2, 3)) + 10 * sd.view(b)).unsqueeze(1), None
+
+    g = torch.Generator().manual_seed(batch)
+    fake, real = torch.randn(batch, 3, 4, 4, generator=g), torch.randn(batch, 3, 4, 4, generator=g) * 2 + 1
+    d = StddevOnly()
+    if batch % min(batch, cap) != 0:                          # the reference's own view() would fail: falls back
+        with pytest.raises(RuntimeError):
+            d(fake)
+        return
+    want_f, want_r = d(fake)[0], d(real)[0]
+    got_f, got_r = d_pair(d, fake, real)
+    torch.testing.assert_close(got_f, want_f)
+    torch.testing.assert_close(got_r, want_r)
