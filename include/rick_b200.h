@@ -20,6 +20,8 @@
  *   rick_decide               train:312-314, 324-330, 368-384 (np.where index sets) + 386-393 (cumulative prune union)
  *   rick_mask_apply           train:427-437, 482-492, 521-539, 566-585 (index_put on param / grad per filter)
  *   rick_adam_mask_ema        the same masks + torch.optim.Adam.step (train:916-925) + accumulate() (train:68-73, 697-698)
+ *   rick_scale_multi          the equalised-lr multipliers ``weight * scale`` / ``bias * lr_mul`` of every EqualConv2d /
+ *                             EqualLinear (gan_training/models/model_probe_tune.py:124, 160-164), one launch per network pass
  *   rick_modconv_*            gan_training/models/model_probe_tune.py:243-284 (ModulatedConv2d: modulate, demodulate,
  *                             grouped conv / transposed conv) -- tcgen05 implicit GEMM, see rick_b200/csrc/conv_tc.cu
  */
