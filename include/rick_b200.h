@@ -22,8 +22,11 @@
  *   rick_adam_mask_ema        the same masks + torch.optim.Adam.step (train:916-925) + accumulate() (train:68-73, 697-698)
  *   rick_scale_multi          the equalised-lr multipliers ``weight * scale`` / ``bias * lr_mul`` of every EqualConv2d /
  *                             EqualLinear (gan_training/models/model_probe_tune.py:124, 160-164), one launch per network pass
- *   rick_modconv_*            gan_training/models/model_probe_tune.py:243-284 (ModulatedConv2d: modulate, demodulate,
- *                             grouped conv / transposed conv) -- tcgen05 implicit GEMM, see rick_b200/csrc/conv_tc.cu
+ *   rick_conv_tc              gan_training/models/model_probe_tune.py:243-284 (ModulatedConv2d: modulate, demodulate,
+ *                             grouped conv / transposed conv) and :122-128 (EqualConv2d) -- the forward AND data-gradient
+ *                             convolutions as one tcgen05 implicit-GEMM kernel, rick_b200/csrc/conv_tc.cu
+ *   rick_conv_wgrad_tc        the weight gradient of the same convolutions (autograd's cuDNN wgrad in the reference),
+ *                             rick_b200/csrc/conv_wgrad.cu
  */
 #ifndef RICK_B200_H
 #define RICK_B200_H
@@ -119,11 +122,16 @@ RICK_API int rick_filter_fim(float* fim, const float* fisher_w, const float* fis
  * two neighbouring order statistics; q is a HOST array; lines is a DEVICE array of nq doubles. */
 RICK_API int rick_percentile(double* lines, const float* fim, int64_t n, const double* q, int nq, rick_stream_t stream);
 
-/* state[i] = (fim>cut ? 1:0) | (prune ? 2:0) | (fine-tune ? 4:0) with cut = lines[0], pruneline = lines[1];
- * closed_low selects the reference's D-skip comparisons (train:382-384).  If zero_mask != NULL it is OR-ed
- * with the prune bit (cumulative prune set, train:386-393); pass reset_zero != 0 on the first round. */
+/* state[i] = (fim>cut ? 1:0) | (prune ? 2:0) | (fine-tune ? 4:0) with cut = lines[0], pruneline = lines[1].
+ * flags bit 0 (RICK_DECIDE_CLOSED_LOW) selects the reference's D-skip comparisons (train:382-384); bit 1
+ * (RICK_DECIDE_COMPARE_F32) compares in float32 against the thresholds rounded to float32 -- NumPy < 2 value-based
+ * casting, what the reference's pinned NumPy 1.23.1 does -- instead of in float64 (NumPy >= 2 promotion).  If
+ * zero_mask != NULL it is OR-ed with the prune bit (cumulative prune set, train:386-393); pass reset_zero != 0 on
+ * the first round. */
+#define RICK_DECIDE_CLOSED_LOW 1
+#define RICK_DECIDE_COMPARE_F32 2
 RICK_API int rick_decide(uint8_t* state, uint8_t* zero_mask, const float* fim, int64_t n, const double* lines,
-                int closed_low, int reset_zero, rick_stream_t stream);
+                int flags, int reset_zero, rick_stream_t stream);
 
 /* One launch for a whole model.  Entry t: param/grad are (rows[t], inner[t]) contiguous float32, state / zero are
  * per-row bytes (NULL = no such set for this tensor).  grad rows with (state&1) or zero are cleared, param rows
@@ -241,11 +249,6 @@ RICK_API int rick_styled_epilogue_bwd_nhwc(void* ga, float* gdemod, float* gbias
                                            const float* noise, int batch, int64_t hw, int channels, float alpha,
                                            float scale, rick_stream_t stream);
 
-/* ------------------------------------------------------------------------------------------- diagnostics
- * Hardware probe used by scripts/debug_conv_tc.py (not part of the product path): out (128,64) = a (128,32) @
- * b[shift:shift+64] (96,32)^T through one tcgen05.mma whose B descriptor starts `shift` rows into a 128B-swizzled tile. */
-RICK_API int rick_debug_umma_shift(float* out, const float* a, const float* b, int shift, int base_offset_mode,
-                                   rick_stream_t stream);
 
 #ifdef __cplusplus
 }

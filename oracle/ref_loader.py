@@ -1,9 +1,8 @@
 """TEST INFRASTRUCTURE ONLY -- load the REAL reference from /root/reference (authoring container only).
 
 ``/root/reference`` does not exist on the GPU box, so nothing that runs there may
-import this module; it is used by ``oracle/make_golden.py`` (which writes
-``tests/golden/*``) and by ``tests/test_oracle_vs_reference.py`` (skipped when the
-tree is absent).
+import this module; it is used only by ``oracle/make_golden.py``, which writes the
+``tests/golden/*`` fixtures that ``tests/test_oracle_golden.py`` checks the oracle against.
 
 Why not ``import op`` / ``import gan_training.models``:
   * ``op/upfirdn2d.py`` and ``op/fused_act.py`` JIT-compile CUDA extensions at import

@@ -88,8 +88,17 @@ def pool(vectors: List[np.ndarray]) -> np.ndarray:
 
 # ------------------------------------------------------------------ decisions (train:302-384)
 
+# NumPy < 2 (the reference pins 1.23.1) compares a float32 array with a float64 scalar after casting the scalar to
+# float32 (value-based casting); NumPy >= 2 promotes the array to float64.  Set to True to restate the former.
+NUMPY1_COMPARE = False
+
+
 def _three_way(fim: np.ndarray, cut, prune, closed_low: bool):
     """freeze / fine-tune / prune index sets.  ``closed_low`` is the D-skip variant (train:382-384)."""
+    if NUMPY1_COMPARE and fim.dtype == np.float32:
+        cut, prune = np.float32(cut), np.float32(prune)
+    else:
+        fim = fim.astype(np.float64, copy=False)
     freeze = np.where(fim > cut)[0]
     if closed_low:
         ft = np.where((fim >= prune) & (fim <= cut))[0]

@@ -2,7 +2,7 @@
 
 Public surface mirrors the reference (yunqing-me/RICK):
   rick_b200.op        upfirdn2d, fused_leaky_relu, FusedLeakyReLU            (reference: op/)
-  rick_b200.model     Generator, Discriminator, ModulatedConv2d, StyledConv, ToRGB, EqualConv2d, ...
+  rick_b200.stylegan2 Generator, Discriminator, ModulatedConv2d, StyledConv, ToRGB, EqualConv2d, ...
                       (reference: gan_training/models/model_probe_tune.py)
   rick_b200.rick      Fisher accumulation -> per-filter FIM -> quantile -> freeze/prune masks -> mask application
                       (reference: train_dynamic_update_prune.py:214-393, 427-437, 521-539)

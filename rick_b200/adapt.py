@@ -14,7 +14,7 @@ idle waiting for the host:
     consumed are the reference's.
 
 All randomness comes from a ``DrawStream`` so that a seeded CPU oracle run can consume the identical sequence
-(tests/test_adapt_parity.py); for throughput runs the stream draws on the device.
+(tests/test_adapt_gpu.py); for throughput runs the stream draws on the device.
 """
 from __future__ import annotations
 

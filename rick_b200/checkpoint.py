@@ -30,9 +30,17 @@ def save(path, adapter):
                 "d_optim": _plain_optim(adapter.d_optim.state_dict())}, path)
 
 
-def load_networks(path, generator, discriminator, g_ema=None, d_ema=None, map_location="cpu") -> dict:
+def read(path, map_location="cpu", trust_pickle: bool = False) -> dict:
+    """``torch.load`` restricted to tensors / containers of primitives (``weights_only=True``): everything the
+    five-key checkpoint holds.  ``trust_pickle=True`` is the explicit opt-in for legacy files that pickled other
+    objects -- unpickling those can execute arbitrary code, so only use it on files you produced."""
+    return torch.load(path, map_location=map_location, weights_only=not trust_pickle)
+
+
+def load_networks(path, generator, discriminator, g_ema=None, d_ema=None, map_location="cpu",
+                  trust_pickle: bool = False) -> dict:
     """The reference's start-up (train:872-879): G from ``"g"``, g_ema from ``"g_ema"``, D and d_ema from ``"d"``."""
-    ckpt = torch.load(path, map_location=map_location, weights_only=False)
+    ckpt = read(path, map_location, trust_pickle)
     generator.load_state_dict(ckpt["g"], strict=False)
     if g_ema is not None:
         g_ema.load_state_dict(ckpt["g_ema"], strict=False)
@@ -42,9 +50,9 @@ def load_networks(path, generator, discriminator, g_ema=None, d_ema=None, map_lo
     return ckpt
 
 
-def resume(path, adapter, map_location="cpu") -> dict:
+def resume(path, adapter, map_location="cpu", trust_pickle: bool = False) -> dict:
     """:func:`load_networks` plus both optimiser states (the keys the reference writes "if you wish to resume")."""
-    ckpt = load_networks(path, adapter.g, adapter.d, adapter.g_ema, adapter.d_ema, map_location)
+    ckpt = load_networks(path, adapter.g, adapter.d, adapter.g_ema, adapter.d_ema, map_location, trust_pickle)
     if "g_optim" in ckpt:
         adapter.g_optim.load_state_dict(ckpt["g_optim"])
     if "d_optim" in ckpt:

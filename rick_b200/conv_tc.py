@@ -40,9 +40,6 @@ _lib._OPTIONAL["rick_to_rgb_nhwc"] = (c_int, [c_void_p, c_void_p, c_void_p, c_vo
                                               c_int, c_void_p])
 
 
-_lib._OPTIONAL["rick_debug_umma_shift"] = (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p])
-
-
 def supported(cin: int, cout: int) -> bool:
     return cin % 32 == 0 and cout % 128 == 0
 

@@ -256,8 +256,14 @@ __global__ void __launch_bounds__(1024) percentile_kernel(double* __restrict__ l
 // ------------------------------------------------------------------------------------------ decisions
 __global__ void __launch_bounds__(256) decide_kernel(uint8_t* __restrict__ state, uint8_t* __restrict__ zero,
                                                      const float* __restrict__ fim, long long n,
-                                                     const double* __restrict__ lines, int closed_low, int reset_zero) {
-    const double cut = lines[0], pr = lines[1];
+                                                     const double* __restrict__ lines, int flags, int reset_zero) {
+    const bool closed_low = (flags & 1) != 0;
+    // NumPy >= 2 compares a float32 array with a float64 scalar in float64; NumPy < 2 (the reference pins 1.23.1,
+    // environment.yml:49) casts the scalar to float32 first (value-based casting).  The two differ only for a FIM
+    // within half a float32 ulp of a threshold.
+    const bool f32_compare = (flags & RICK_DECIDE_COMPARE_F32) != 0;
+    const double cut = f32_compare ? (double)(float)lines[0] : lines[0];
+    const double pr = f32_compare ? (double)(float)lines[1] : lines[1];
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x) {
         const double f = (double)fim[i];
@@ -362,14 +368,14 @@ extern "C" int rick_percentile(double* lines, const float* fim, int64_t n, const
 }
 
 extern "C" int rick_decide(uint8_t* state, uint8_t* zero_mask, const float* fim, int64_t n, const double* lines,
-                           int closed_low, int reset_zero, rick_stream_t stream) {
+                           int flags, int reset_zero, rick_stream_t stream) {
     using namespace rick;
     if (!state || !fim || !lines || n < 0) return RICK_ERR_INVALID_ARGUMENT;
     if (n == 0) return RICK_OK;
     long long blocks = ceil_div(n, 256);
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     decide_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(state, zero_mask, fim, n, lines,
-                                                                                    closed_low, reset_zero);
+                                                                                    flags, reset_zero);
     RICK_CHECK_LAUNCH();
     return RICK_OK;
 }

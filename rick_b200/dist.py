@@ -78,12 +78,9 @@ class FeatureStats:
         return mu, cov
 
 
-def allreduce_mean_(tensors: Sequence[torch.Tensor], bucket_bytes: int = 64 << 20):
-    """In-place average of ``tensors`` over ranks in flat buckets (NVSwitch makes cost per-launch, not per-link bound:
-    few large buckets)."""
-    w = world_size()
-    if w == 1:
-        return
+def _allreduce_buckets_(tensors: Sequence[torch.Tensor], scale: float, bucket_bytes: int):
+    """In-place all-reduce (SUM) of ``tensors`` in flat buckets, multiplied by ``scale`` afterwards when it is not 1
+    (NVSwitch makes cost per-launch, not per-link bound: few large buckets)."""
     bucket: List[torch.Tensor] = []
     size = 0
 
@@ -91,9 +88,16 @@ def allreduce_mean_(tensors: Sequence[torch.Tensor], bucket_bytes: int = 64 << 2
         nonlocal bucket, size
         if not bucket:
             return
+        if len(bucket) == 1 and bucket[0].is_contiguous():       # a flat buffer already: reduce it where it lies
+            dist.all_reduce(bucket[0], op=dist.ReduceOp.SUM)
+            if scale != 1.0:
+                bucket[0].mul_(scale)
+            bucket, size = [], 0
+            return
         flat = torch.cat([t.reshape(-1) for t in bucket])
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        flat.mul_(1.0 / w)
+        if scale != 1.0:
+            flat.mul_(scale)
         off = 0
         for t in bucket:
             n = t.numel()
@@ -111,15 +115,20 @@ def allreduce_mean_(tensors: Sequence[torch.Tensor], bucket_bytes: int = 64 << 2
     flush()
 
 
-def allreduce_sum_(tensors: Iterable[torch.Tensor], bucket_bytes: int = 128 << 20):
-    """In-place SUM over ranks (Fisher accumulators)."""
+def allreduce_mean_(tensors: Sequence[torch.Tensor], bucket_bytes: int = 64 << 20):
+    """In-place average of ``tensors`` over ranks."""
     w = world_size()
     if w == 1:
         return
-    ts = [t for t in tensors]
-    allreduce_mean_(ts, bucket_bytes)
-    for t in ts:
-        t.mul_(float(w))
+    _allreduce_buckets_(tensors, 1.0 / w, bucket_bytes)
+
+
+def allreduce_sum_(tensors: Iterable[torch.Tensor], bucket_bytes: int = 128 << 20):
+    """In-place SUM over ranks (Fisher accumulators): the exact sum, no scaling pass (a mean followed by ``* world``
+    would round twice for world sizes that are not powers of two and could move filters across a percentile)."""
+    if world_size() == 1:
+        return
+    _allreduce_buckets_(list(tensors), 1.0, bucket_bytes)
 
 
 def barrier():

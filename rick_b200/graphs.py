@@ -15,15 +15,25 @@ before the replay:
 
 The Fisher round (once per ``fisher_freq`` iterations) replays a sixth graph -- its per-image body: G forward, joint D
 pass, two backward passes, grad**2 accumulation -- and keeps the exchange step, the percentile and the mask update eager
-(164 -> 50 ms per round at 256 px).  Capturing a graph runs its body twice as warm-up; for the training sub-steps those
-are real optimiser steps, for the Fisher body the accumulators are cleared afterwards.  Under torchrun (world_size > 1)
-the DDP gradient all-reduce is captured inside the graphs (NCCL supports stream capture), so every rank replays the
-same sequence of collectives.
+(164 -> 50 ms per round at 256 px).  Capturing a graph runs its body twice as warm-up; everything those executions
+touch (the four networks, both optimisers' moments and step counts, the path-length mean, the Fisher accumulators, the
+CUDA RNG state) is snapshotted before and restored after, so capture is invisible to the training trajectory:
+iteration 0 of a graphed run starts from exactly the state an eager run starts from (``prepare()`` captures every
+graph up front).  Under torchrun (world_size > 1) the DDP gradient all-reduce is captured inside the graphs (NCCL
+supports stream capture), so every rank replays the same sequence of collectives.
+
+Randomness.  Throughput mode (default): latents and per-layer noise are drawn by the device RNG inside the graphs; the
+style-mixing decision and crossover index come from the ``draws`` stream handed to ``step`` (or, without one, from a
+generator owned by the adapter and seeded at construction) -- never from the global ``random`` module.
+``explicit_inputs=True`` (parity runs): latents, per-layer noise and the path-length image noise are static buffers
+filled from ``draws`` in the reference's order before each replay, so a CPU oracle consuming the same ``DrawStream``
+sees identical inputs.
 """
 from __future__ import annotations
 
+import math
 import random
-from typing import Dict
+from typing import Dict, List, Tuple
 
 import torch
 from torch import autograd, optim
@@ -36,7 +46,7 @@ from .fused import FusedGenerator
 
 class GraphedRickAdapter(RickAdapter):
     def __init__(self, cfg: AdaptConfig, generator, discriminator, g_ema, d_ema, fused_generator: bool = True,
-                 fused_optim: bool = True):
+                 fused_optim: bool = True, explicit_inputs: bool = False, seed: int = 0):
         super().__init__(cfg, generator, discriminator, g_ema, d_ema, fused_adam=True, fused_generator=False,
                          fused_optim=fused_optim)
         # world_size > 1: the gradient all-reduce (NCCL) is recorded inside the graphs, between backward and Adam
@@ -56,6 +66,16 @@ class GraphedRickAdapter(RickAdapter):
         self._f_real = torch.zeros(1, 3, cfg.size, cfg.size, device=dev)
         self._inject = {k: torch.full((), generator.n_latent, dtype=torch.long, device=dev) for k in ("d", "g", "path")}
         self._layer = torch.arange(generator.n_latent, device=dev).view(1, -1, 1)
+        self.explicit_inputs = bool(explicit_inputs)
+        self._rng = random.Random(seed)                 # mixing decisions when step() is given no draw stream
+        pb = max(1, cfg.batch // cfg.path_batch_shrink)
+        self._batch_of = {"d": cfg.batch, "g": cfg.batch, "path": pb}
+        if self.explicit_inputs:
+            log_size = int(math.log2(cfg.size))
+            shapes = [4] + [2 ** i for i in range(3, log_size + 1) for _ in range(2)]
+            self._z = {k: torch.zeros(2, b, cfg.latent, device=dev) for k, b in self._batch_of.items()}
+            self._noise = {k: [torch.zeros(b, 1, r, r, device=dev) for r in shapes] for k, b in self._batch_of.items()}
+            self._path_noise = torch.zeros(pb, 3, cfg.size, cfg.size, device=dev)
         self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}
         self._outs: Dict[str, Dict[str, torch.Tensor]] = {}
         self._graph_launches: Dict[str, int] = {}      # rick_b200 kernel nodes recorded in each graph
@@ -66,9 +86,12 @@ class GraphedRickAdapter(RickAdapter):
     # ---- graph bodies -----------------------------------------------------------------------------------
     def _latent(self, batch: int, key: str) -> torch.Tensor:
         cfg = self.cfg
-        z = torch.randn(2, batch, cfg.latent, device=self.device)
+        z = self._z[key] if self.explicit_inputs else torch.randn(2, batch, cfg.latent, device=self.device)
         w1, w2 = self.g.style(z[0]), self.g.style(z[1])
         return torch.where(self._layer < self._inject[key], w1.unsqueeze(1), w2.unsqueeze(1))
+
+    def _layer_noise(self, key: str):
+        return self._noise[key] if self.explicit_inputs else None
 
     def _body_d(self):
         cfg = self.cfg
@@ -76,9 +99,9 @@ class GraphedRickAdapter(RickAdapter):
             latent = self._latent(cfg.batch, "d")
             if self.fg is not None:
                 self.fg.refresh()
-                fake_img, _ = self.fg([latent], input_is_latent=True)
+                fake_img, _ = self.fg([latent], input_is_latent=True, noise=self._layer_noise("d"))
             else:
-                fake_img, _ = self.g([latent], input_is_latent=True)
+                fake_img, _ = self.g([latent], input_is_latent=True, noise=self._layer_noise("d"))
         fake_pred, real_pred = d_pair(self.d, fake_img, self._real)
         d_loss = d_logistic_loss(real_pred, fake_pred)
         self.d.zero_grad(set_to_none=True)
@@ -102,7 +125,7 @@ class GraphedRickAdapter(RickAdapter):
     def _body_g(self):
         cfg = self.cfg
         latent = self._latent(cfg.batch, "g")
-        fake_img, _ = self.g([latent], input_is_latent=True)
+        fake_img, _ = self.g([latent], input_is_latent=True, noise=self._layer_noise("g"))
         fake_pred, _ = self.d(fake_img)
         g_loss = g_nonsaturating_loss(fake_pred)
         self.g.zero_grad(set_to_none=True)
@@ -115,9 +138,9 @@ class GraphedRickAdapter(RickAdapter):
         cfg = self.cfg
         pb = max(1, cfg.batch // cfg.path_batch_shrink)
         latent = self._latent(pb, "path")
-        fake_img, latents = self.g([latent], input_is_latent=True, return_latents=True)
-        path_loss, path_mean, path_lengths = g_path_regularize(fake_img, latents, self.mean_path_length,
-                                                               torch.randn_like(fake_img))
+        fake_img, latents = self.g([latent], input_is_latent=True, return_latents=True, noise=self._layer_noise("path"))
+        path_noise = self._path_noise if self.explicit_inputs else torch.randn_like(fake_img)
+        path_loss, path_mean, path_lengths = g_path_regularize(fake_img, latents, self.mean_path_length, path_noise)
         self.g.zero_grad(set_to_none=True)
         weighted = cfg.path_regularize * cfg.g_reg_every * path_loss
         if cfg.path_batch_shrink:
@@ -157,22 +180,73 @@ class GraphedRickAdapter(RickAdapter):
             self._run("fisher")
         self._fisher_end()
 
+    # ---- state that a graph body mutates: snapshotted around warm-up + capture ---------------------------------
+    def _mutable_state(self) -> List[torch.Tensor]:
+        ts: List[torch.Tensor] = []
+        for net in (self.g, self.d, self.g_ema, self.d_ema):
+            ts += [p.data for p in net.parameters()]
+        for opt in (self.g_optim, self.d_optim):
+            if self.fused_optim:
+                ts += [opt.steps] + list(opt.exp_avg.values()) + list(opt.exp_avg_sq.values())
+        ts += [self.mean_path_length] + list(self.acc_g.acc) + list(self.acc_d.acc)
+        return ts
+
+    def _snapshot(self):
+        snap = [(t, t.clone()) for t in self._mutable_state()]
+        grads = [(p, p.grad) for net in (self.g, self.d, self.g_ema, self.d_ema) for p in net.parameters()]
+        torch_adam = None
+        if not self.fused_optim:           # torch.optim.Adam creates its state lazily: remember what existed
+            torch_adam = [{id(p): {k: (v.clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+                           for p, st in opt.state.items()} for opt in (self.g_optim, self.d_optim)]
+        return snap, grads, torch_adam, torch.cuda.get_rng_state(self.device)
+
+    @torch.no_grad()
+    def _restore(self, state):
+        snap, grads, torch_adam, rng = state
+        for t, saved in snap:
+            t.copy_(saved)
+        for p, g in grads:
+            p.grad = g
+        if torch_adam is not None:
+            for opt, before in zip((self.g_optim, self.d_optim), torch_adam):
+                for p, st in opt.state.items():
+                    old = before.get(id(p))
+                    for k, v in st.items():
+                        if torch.is_tensor(v):          # in place: the graph recorded these very tensors
+                            v.copy_(old[k]) if old is not None else v.zero_()
+        torch.cuda.set_rng_state(rng, self.device)
+
     def _ensure(self, key: str):
-        if key not in self._graphs:
-            body = getattr(self, "_body_" + key)
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for _ in range(2):          # warm-up executions on a side stream (these are real training steps)
-                    body()
-            torch.cuda.current_stream().wait_stream(side)
-            from . import _lib
-            graph = torch.cuda.CUDAGraph()
-            n0 = _lib.lib().rick_launch_count()
-            with torch.cuda.graph(graph):
-                outs = body()
-            self._graph_launches[key] = int(_lib.lib().rick_launch_count() - n0)   # launches recorded, not executed
-            self._graphs[key], self._outs[key] = graph, outs
+        """Capture graph ``key`` (no-op when it exists).  The two warm-up executions the capture needs are rolled back:
+        parameters, optimiser state, EMA copies, path-length mean, Fisher accumulators and the RNG state are the same
+        after this call as before it."""
+        if key in self._graphs:
+            return
+        body = getattr(self, "_body_" + key)
+        state = self._snapshot()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):              # warm-up executions on a side stream (rolled back below)
+                body()
+        torch.cuda.current_stream().wait_stream(side)
+        from . import _lib
+        graph = torch.cuda.CUDAGraph()
+        n0 = _lib.lib().rick_launch_count()
+        with torch.cuda.graph(graph):
+            outs = body()
+        self._graph_launches[key] = int(_lib.lib().rick_launch_count() - n0)   # launches recorded, not executed
+        self._graphs[key], self._outs[key] = graph, outs
+        self._restore(state)
+
+    def prepare(self, fisher: bool = True):
+        """Capture every graph now.  Leaves the training state untouched (see ``_ensure``)."""
+        if fisher:
+            self._fisher_begin(1)
+            self._ensure("fisher")
+        for key in ("d", "r1", "g", "path", "ema"):
+            self._ensure(key)
+        return self
 
     def _run(self, key: str):
         self._ensure(key)
@@ -180,24 +254,47 @@ class GraphedRickAdapter(RickAdapter):
         self.replayed_launches += self._graph_launches[key]
         return self._outs[key]
 
-    def _set_inject(self, key: str):
+    def _draw_inputs(self, key: str, draws):
+        """Everything random one sub-step consumes, in the reference's order (train:397, 501, 548; model_probe_tune.py:556):
+        mixing decision, latents, crossover index, then per-layer noise.  Throughput mode only takes the mixing decision
+        and the index from the host stream; latents / noise are drawn on the device inside the graph."""
         cfg = self.cfg
         n = self.g.n_latent
-        v = random.randint(1, n - 1) if (cfg.mixing > 0 and random.random() < cfg.mixing) else n
-        self._inject[key].fill_(v)
+        b = self._batch_of[key]
+        if self.explicit_inputs:
+            if draws is None:
+                raise RuntimeError("GraphedRickAdapter(explicit_inputs=True).step needs a DrawStream")
+            z = draws.mixing_latents(b, cfg.latent, cfg.mixing)
+            inject = draws.randint(1, n - 1) if len(z) == 2 else n
+            self._z[key][0].copy_(z[0], non_blocking=True)
+            if len(z) == 2:
+                self._z[key][1].copy_(z[1], non_blocking=True)
+            for dst, src in zip(self._noise[key], draws.layer_noise(b, cfg.size)):
+                dst.copy_(src, non_blocking=True)
+        elif draws is not None:
+            mix = cfg.mixing > 0 and draws.uniform() < cfg.mixing
+            inject = draws.randint(1, n - 1) if mix else n
+        else:
+            mix = cfg.mixing > 0 and self._rng.random() < cfg.mixing
+            inject = self._rng.randint(1, n - 1) if mix else n
+        self._inject[key].fill_(inject)
 
     def step(self, i: int, real_img: torch.Tensor, draws=None, explicit_layer_noise: bool = False):
+        """One iteration (same sub-steps and order as ``RickAdapter.step``).  ``explicit_layer_noise`` is implied by
+        ``explicit_inputs`` and ignored otherwise (throughput mode draws per-layer noise on the device)."""
         cfg = self.cfg
         self._real.copy_(real_img, non_blocking=True)
         out: Dict[str, torch.Tensor] = {}
-        self._set_inject("d")
+        self._draw_inputs("d", draws)
         out.update(self._run("d"))
         if i % cfg.d_reg_every == 0:
             out.update(self._run("r1"))
-        self._set_inject("g")
+        self._draw_inputs("g", draws)
         out.update(self._run("g"))
         if i % cfg.g_reg_every == 0:
-            self._set_inject("path")
+            self._draw_inputs("path", draws)
+            if self.explicit_inputs:
+                self._path_noise.copy_(draws.normal(*self._path_noise.shape), non_blocking=True)
             out.update(self._run("path"))
         self._run("ema")
-        return out
+        return {k: v.clone() for k, v in out.items()} if self.explicit_inputs else out

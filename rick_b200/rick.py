@@ -135,7 +135,12 @@ class FilterMasks:
     ``state[key]`` holds per-filter bits (1 freeze, 2 prune, 4 fine-tune); ``zero[key]`` is the cumulative prune
     union (train:386-393).  Keys are parameter names, exactly the keys of the reference's idx_* dicts."""
 
-    def __init__(self, layers: List[FilterLayer], device):
+    def __init__(self, layers: List[FilterLayer], device, numpy1_compare: bool = False):
+        """``numpy1_compare``: compare float32 FIMs against the float64 thresholds the way NumPy < 2 does (threshold
+        cast to float32 first -- the reference pins NumPy 1.23.1); default is NumPy >= 2 promotion (float64), which is
+        what the golden masks of this repository were generated under (NumPy 2.3.5).  The two differ only for a filter
+        whose FIM lies within half a float32 ulp of a threshold."""
+        self.numpy1_compare = bool(numpy1_compare)
         self.layers = layers
         self.device = torch.device(device)
         self.groups: Dict[str, int] = {}
@@ -176,7 +181,8 @@ class FilterMasks:
                 sl = slice(l.offset, l.offset + l.rows)
                 _lib.check(lib.rick_decide(self._state[l.group][sl].data_ptr(), self._zero[l.group][sl].data_ptr(),
                                            self.fim[l.group][sl].data_ptr(), l.rows, self.lines[l.group].data_ptr(),
-                                           int(l.closed_low), int(self.rounds == 0), s), "rick_decide")
+                                           int(l.closed_low) | (2 if self.numpy1_compare else 0), int(self.rounds == 0), s),
+                           "rick_decide")
         self.rounds += 1
 
     def apply(self, named_params: Dict[str, torch.nn.Parameter], force: bool = False):

@@ -28,6 +28,8 @@ def main():
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--seed", type=int, default=1000)
     ap.add_argument("--ckpt", type=str, default=None, help="reference checkpoint with a 'g_ema' state_dict")
+    ap.add_argument("--trust-pickle", action="store_true",
+                    help="allow full unpickling of --ckpt (legacy files; executes code embedded in the file)")
     args = ap.parse_args()
     rank, world, local_rank = rdist.init_from_env()
     device = torch.device("cuda", local_rank)
@@ -35,7 +37,8 @@ def main():
     torch.manual_seed(1)
     G = sg.Generator(args.size, 512, 8)
     if args.ckpt:
-        G.load_state_dict(torch.load(args.ckpt, map_location="cpu")["g_ema"], strict=False)
+        from .checkpoint import read
+        G.load_state_dict(read(args.ckpt, trust_pickle=args.trust_pickle)["g_ema"], strict=False)
     G = G.to(device).eval()
     stats = rdist.FeatureStats(3 * 8 * 8, device)
     it = generate_samples(G, args.n, args.batch, rank=rank, world=world, seed=args.seed, fused=True)

@@ -56,22 +56,6 @@ run("random 3x3", 2, 16, 16, 64, 128, 3, 1, 1, x, wgt)
 x = torch.randn(2, 64, 17, 17, device=dev)
 run("random 3x3 stride 2", 2, 17, 17, 64, 128, 3, 2, 0, x, wgt)
 
-# probe 7: may a swizzled K-major operand start at an arbitrary row? (decides the halo-reuse design)
-from rick_b200 import _lib
-a = torch.randn(128, 32, device=dev)
-bb = torch.randn(96, 32, device=dev)
-out = torch.empty(128, 64, device=dev)
-for mode in (0, 1):
-    res = []
-    for shift in (0, 1, 2, 3, 5, 7, 8, 9, 16, 17, 32):
-        out.zero_()
-        st = _lib.lib().rick_debug_umma_shift(out.data_ptr(), a.data_ptr(), bb.data_ptr(), shift, mode,
-                                              torch.cuda.current_stream().cuda_stream)
-        torch.cuda.synchronize()
-        want = a @ bb[shift:shift + 64].T
-        res.append((shift, st, round(((out - want).abs().max() / want.abs().max()).item(), 4)))
-    print(f"umma row-shift probe, base_offset_mode={mode}: (shift, status, rel err) =", res, flush=True)
-
 # timing at a generator-like shape (batch 16, 64x64, 512 -> 512)
 b, h, cin, cout = 16, 64, 512, 512
 x = torch.randn(b, h, h, cin, device=dev)

@@ -78,9 +78,30 @@ def test_generator256_vs_golden(golden):
     with torch.no_grad():
         img, _ = G([lat[:2]], randomize_noise=False)
     assert img.shape == (2, 3, 256, 256)
-    assert _img_err(img[:, :, ::4, ::4], gold["img_sub4"]) < IMG_TOL
+    abs_err = (img[:, :, ::4, ::4].cpu().double() - torch.as_tensor(gold["img_sub4"]).double()).abs().max().item()
     mean, std, amax = gold["img_moments"]
+    print(f"256 px image: max-abs error {abs_err:.3e} on a random-init image with max |pixel| {amax:.2f} "
+          f"(= {abs_err / amax:.2e} of full scale; a trained generator's image spans [-1, 1])")
+    assert _img_err(img[:, :, ::4, ::4], gold["img_sub4"]) < IMG_TOL
     assert abs(img.double().mean().item() - mean) < 1e-2 * amax and abs(img.double().std().item() - std) < 1e-2 * amax
+    # D(256) on our image against the reference's logits for ITS image: G's and D's TF32 error compound
+    with torch.no_grad():
+        logits, _ = D(img)
+    np.testing.assert_allclose(logits.cpu().numpy(), gold["logits"], rtol=3e-2, atol=3e-2)
+
+
+def test_fused_generator256_vs_golden(golden):
+    """The tcgen05 executor (rick_b200.fused.FusedGenerator: sample generation and the D step's fake batch) on the same
+    golden image, with the absolute error printed."""
+    from rick_b200.fused import FusedGenerator
+    gold = golden("g256_golden.npz")
+    G, D, gp, dp = _build(256, 1, 2)
+    lat = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "fisher_latents.npy"))).cuda()
+    img, _ = FusedGenerator(G)([lat[:2]], randomize_noise=False)
+    abs_err = (img[:, :, ::4, ::4].cpu().double() - torch.as_tensor(gold["img_sub4"]).double()).abs().max().item()
+    amax = gold["img_moments"][2]
+    print(f"256 px image (tcgen05 executor): max-abs error {abs_err:.3e}, max |pixel| {amax:.2f} ({abs_err / amax:.2e} of full scale)")
+    assert _img_err(img[:, :, ::4, ::4], gold["img_sub4"]) < IMG_TOL
 
 
 def test_fp32_mode_matches_oracle_tightly():

@@ -105,6 +105,44 @@ def test_near_tie_thresholds():
         assert np.array_equal(gfr[k], fr[k]) and np.array_equal(gft[k], ft[k]) and np.array_equal(gpr[k], pr[k]), k
 
 
+def test_numpy1_comparison_rule_flag():
+    """The reference pins NumPy 1.23.1, where ``float32_array > float64_scalar`` compares in float32 (value-based casting);
+    NumPy >= 2 compares in float64.  ``FilterMasks(numpy1_compare=True)`` / RICK_DECIDE_COMPARE_F32 restate the former.
+    Built so the rules disagree: an interpolated percentile lies strictly between two adjacent float32 FIM values, so in
+    float64 one value is above the line and in float32 (line rounded onto one of the two) it is not."""
+    from rick_b200 import rick
+    fg = synth.fisher_g(55, size=32)
+    cg = _to_cuda(fg)
+    res = {}
+    for flag in (False, True):
+        masks = rick.FilterMasks(rick.generator_layers(cg), "cuda", numpy1_compare=flag)
+        masks.update(cg, 40.0, 0.1)
+        ro.NUMPY1_COMPARE = flag
+        try:
+            fr, ft, pr, lines = ro.decide_g(fg, 40.0, 0.1, n_convs=6)
+        finally:
+            ro.NUMPY1_COMPARE = False
+        gfr, gft, gpr, _ = masks.index_sets()
+        for k in fr:
+            assert np.array_equal(gfr[k], fr[k]) and np.array_equal(gft[k], ft[k]) and np.array_equal(gpr[k], pr[k]), (flag, k)
+        res[flag] = (gfr, gpr)
+    # direct kernel check on a constructed disagreement
+    from rick_b200 import _lib
+    lo = np.float32(1.0)
+    hi = np.nextafter(lo, np.float32(2))
+    line = float(lo) + 0.75 * (float(hi) - float(lo))          # rounds to hi in float32
+    fim = torch.tensor([lo, hi], dtype=torch.float32, device="cuda")
+    lines = torch.tensor([line, -1.0], dtype=torch.float64, device="cuda")
+    out = {}
+    for flags in (0, 2):
+        st = torch.zeros(2, dtype=torch.uint8, device="cuda")
+        _lib.check(_lib.lib().rick_decide(st.data_ptr(), None, fim.data_ptr(), 2, lines.data_ptr(), flags, 1,
+                                          torch.cuda.current_stream().cuda_stream), "rick_decide")
+        out[flags] = (st.cpu().numpy() & 1).tolist()
+    assert out[0] == [0, 1]           # float64: hi > line
+    assert out[2] == [0, 0]           # float32: hi > float32(line) == hi is False
+
+
 def test_fisher_accumulate_matches_numpy_float32_order():
     from rick_b200 import rick
     g = torch.Generator().manual_seed(3)
