@@ -177,7 +177,8 @@ RICK_API int rick_scale_multi(float* const* out, const float* const* in, const f
  * stride-2 transposed convolution).  Phase-local output position (m, n), m < rows, n < cols, reads input pixel
  * (m*in_stride + dy[t], n*in_stride + dx[t]) for each tap t (out-of-range pixels count as zero) with weight matrix
  * wt[widx[t]], and is written to output pixel (m*out_stride + out_y0, n*out_stride + out_x0).
- * Requirements: cin % 32 == 0, cout % 128 == 0, pointers 16-byte aligned. */
+ * Requirements: cin % 32 == 0, cout % 32 == 0 (tiles of 128 output channels; a partial tile rides on TMA zero fill),
+ * pointers 16-byte aligned. */
 typedef struct rick_conv_phase {
     int n_taps;
     int dy[9], dx[9], widx[9];
@@ -211,6 +212,51 @@ typedef struct rick_conv_epilogue {
 
 RICK_API int rick_conv_tc(void* out, const void* xm, const void* wt, const rick_conv_geom* geom,
                           const rick_conv_epilogue* epilogue, rick_stream_t stream);
+
+/* The same kernel with the weight operand described by strides (in elements), so that ONE weight tensor in memory
+ * serves both directions -- there is no transposed or re-packed copy:
+ *   forward        GEMM-M = the layer's output channels, GEMM-K = its input channels.  For a (Cout, Cin, k, k) weight
+ *                  stored channels-last ([Cout][k][k][Cin]): stride_m = k*k*Cin, stride_k = 1, stride_tap = Cin.
+ *   data gradient  (autograd's cuDNN dgrad in the reference): geom describes the transposed problem -- geom->cout is the
+ *                  layer's Cin, geom->cin its Cout, the taps are mirrored -- over the SAME memory: stride_m = 1,
+ *                  stride_k = k*k*Cin, stride_tap = Cin.  stride_m == 1 makes the weight an MN-major UMMA operand.
+ * Element (m, k, tap) of the operand is ptr[m*stride_m + k*stride_k + widx*stride_tap].  Exactly one of stride_m /
+ * stride_k must be 1, the others multiples of 4 elements.  geom->cout % 32 == 0, geom->cin % 32 == 0. */
+typedef struct rick_conv_weight {
+    const void* ptr;
+    int64_t stride_m, stride_k, stride_tap;
+} rick_conv_weight;
+
+RICK_API int rick_conv_tc_w(void* out, const void* xm, const rick_conv_weight* weight, const rick_conv_geom* geom,
+                            const rick_conv_epilogue* epilogue, rick_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------- tcgen05 weight gradient
+ * dW of the convolutions above (in the reference: autograd's cuDNN wgrad behind model_probe_tune.py:122-128, 265, 274,
+ * 280).  For each tap t < n_taps:
+ *     dW[t][co][ci] = scale * sum_{b, m < rows, n < cols}  g[b, m*g_stride + gy[t], n*g_stride + gx[t], co]
+ *                                                         * x[b, m*x_stride + xy[t], n*x_stride + xx[t], ci]
+ * with g (batch, g_h, g_w, cout) and x (batch, x_h, x_w, cin) NHWC fp32; pixels outside either tensor count as zero.
+ *   stride-1 / stride-s convolution (pad p):  (m, n) runs over the OUTPUT pixels; g_stride = 1, gy = gx = 0,
+ *                                             x_stride = s, xy[t] = ky - p, xx[t] = kx - p
+ *   stride-2 transposed convolution:          (m, n) runs over the INPUT pixels; x_stride = 1, xy = xx = 0,
+ *                                             g_stride = 2, gy[t] = ky, gx[t] = kx
+ * The result is written as dw[co*stride_co + ci*stride_ci + t*stride_tap] (element strides), i.e. directly in the
+ * parameter's memory layout.  Partial sums over pixel ranges are folded in a fixed order: deterministic.
+ * workspace: rick_conv_wgrad_workspace(geom) bytes (negative = unsupported geometry).  cout % 32 == 0, cin % 32 == 0. */
+typedef struct rick_wgrad_geom {
+    int batch;
+    int g_h, g_w, cout;
+    int x_h, x_w, cin;
+    int n_taps;
+    int gy[9], gx[9], xy[9], xx[9];
+    int g_stride, x_stride;
+    int rows, cols;
+} rick_wgrad_geom;
+
+RICK_API int64_t rick_conv_wgrad_workspace(const rick_wgrad_geom* geom);
+RICK_API int rick_conv_wgrad_tc(void* dw, int64_t stride_co, int64_t stride_ci, int64_t stride_tap, const void* g,
+                                const void* x, const rick_wgrad_geom* geom, void* workspace, float scale,
+                                rick_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------- NHWC companions
  * rick_blur_nhwc: 4x4 FIR, up = down = 1, pads (pad0, pad1) on both axes, over x (batch, in_h, in_w, channels) fp32

@@ -1,15 +1,20 @@
-"""Convolution dispatch for the StyleGAN2 stack.
+"""Convolutions of the StyleGAN2 stack, forward AND backward, on the tcgen05 kernels of this package.
 
-Two executors sit behind ``modulated_conv2d`` / ``conv2d``:
+``_Conv`` / ``_ConvGrad`` are autograd Functions over three primitives
 
-  * ``tc``     the hand-written tcgen05 / TMEM / TMA implicit-GEMM kernels of this package
-               (rick_b200/csrc/conv_tc.cu via the C ABI) -- TF32 operands, fp32 accumulation in tensor memory,
-               demodulation + noise + bias + leaky-ReLU fused into the epilogue.  Used wherever it is implemented
-               (see ``tc_supported``); the status table lives in DESIGN.md.
-  * ``cudnn``  ATen / cuDNN dense convolutions on the SHARED weight (``groups = 1``: the modulation is folded into
-               the activations and the demodulation into the output, so this is a plain library conv, not the
-               reference's grouped conv on materialised per-sample weights).  It is the differentiable path
-               (first and second derivatives for R1 / path-length) until the tcgen05 dgrad / wgrad kernels land.
+    fprop(x, w)        y  = conv(x, w)                      rick_conv_tc_w      (csrc/conv_tc.cu)
+    dgrad(g, w)        gx = conv^T(g, w)                    rick_conv_tc_w, the weight read transposed in place
+    wgrad(g, x)        gw = sum_pixels g (x) x              rick_conv_wgrad_tc  (csrc/conv_wgrad.cu)
+
+for ordinary (stride 1 / 2) and stride-2 transposed convolutions -- every convolution ModulatedConv2d (in its algebraic
+form: the modulation folded into the activations, the demodulation into the output, model_probe_tune.py:243-284) and
+EqualConv2d (:122-128) run.  The reference gets these from cuDNN through autograd; here they are TF32 tcgen05 implicit
+GEMMs on channels-last activations and channels-last weights, with no re-packed or transposed weight copies.
+
+A primitive falls back to the ATen library call only when the kernels do not cover its shape (channel counts that are
+not multiples of 32, e.g. D's 3-channel from-RGB layer; non-channels-last operands) or when TF32 math is switched off
+(``torch.backends.cudnn.allow_tf32 = False``, which tests use to isolate the other kernels in fp32).
+``RICK_CONV_BACKEND=cudnn`` forces the library, ``=tc`` makes an uncovered shape an error.  ``launch_stats`` counts both.
 
 There is no CPU executor: inputs must be CUDA tensors.
 """
@@ -21,42 +26,130 @@ from typing import Optional
 import torch
 from torch.nn import functional as F
 
+from . import conv_tc as _ct
 from .op import styled as _styled
 
 _FORCE = os.environ.get("RICK_CONV_BACKEND", "")   # "", "cudnn" or "tc" (tests use it to pin an executor)
+launch_stats = {"tc": 0, "library": 0}
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# library convolution with explicit first- and second-order gradients
+# primitives
 # ---------------------------------------------------------------------------------------------------------------
-# R1 (train:462-493) and the path-length regulariser (train:546-589) differentiate THROUGH a backward pass.  Left to
-# autograd's generic double-backward formula, the weight-gradient term of a convolution is evaluated as a forward
-# convolution whose "filter" is a whole feature map (a (128, 1, 256, 256) input against a (128, 1, 256, 256) weight at
-# 256 px): the library has no tensor-core kernel for that and one path-length iteration spent 10 of its 33 ms there
-# (round-1 torch.profiler run, scripts/profile_path.py).  Written out, every term of the second derivative is again a
-# forward conv, a data gradient or a weight gradient with ordinary shapes:
-#     y  = conv(x, w)          gx = dgrad(g, w)          gw = wgrad(g, x)
-#     d<ggx, gx>/dg = conv(ggx, w)      d<ggx, gx>/dw = wgrad(g, ggx)
-#     d<ggw, gw>/dg = conv(x, ggw)      d<ggw, gw>/dx = dgrad(g, ggw)
-# so the two Functions below call themselves / each other and stay differentiable to any order.
 def _conv_args(stride: int, padding: int, transposed: bool):
     return [stride, stride], [padding, padding], [1, 1], transposed, [0, 0], 1
 
 
+def _is_cl(t: torch.Tensor) -> bool:
+    return t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last)
+
+
+def _nhwc(t: torch.Tensor) -> torch.Tensor:
+    """physical (B, H, W, C) view of a channels-last (B, C, H, W) tensor"""
+    return t.permute(0, 2, 3, 1)
+
+
+def _use_tc(x: torch.Tensor, w_shape, cfg, m_ch: int, k_ch: int) -> bool:
+    """Shape / mode test shared by the three primitives.  ``m_ch`` / ``k_ch``: the channel counts that become GEMM-M
+    (or N) and GEMM-K of the call."""
+    stride, padding, transposed = cfg
+    kh, kw = w_shape[2], w_shape[3]
+    ok = (_FORCE != "cudnn" and torch.backends.cudnn.allow_tf32 and x.is_cuda and x.dtype == torch.float32
+          and kh == kw and kh in (1, 3) and m_ch % 32 == 0 and k_ch % 32 == 0
+          and ((not transposed and stride in (1, 2)) or (transposed and stride == 2 and padding == 0 and kh == 3))
+          and x.numel() > 0 and x.shape[0] * x.shape[2] * x.shape[3] * max(m_ch, k_ch) < 2 ** 31)
+    if not ok and _FORCE == "tc":
+        raise RuntimeError(f"RICK_CONV_BACKEND=tc but the tcgen05 kernels do not cover conv {tuple(w_shape)} {cfg} on "
+                           f"{tuple(x.shape)}")
+    return ok
+
+
+def _cl(t: torch.Tensor) -> torch.Tensor:
+    return t if _is_cl(t) else t.contiguous(memory_format=torch.channels_last)
+
+
+def _fprop(x, w, cfg):
+    stride, padding, transposed = cfg
+    co, ci, k, _ = w.shape
+    if _use_tc(x, w.shape, cfg, co, ci):
+        launch_stats["tc"] += 1
+        x, w = _cl(x), _cl(w)
+        b, _, h, wd = x.shape
+        geom = (_ct.geom_conv_transpose_s2(b, h, wd, ci, co, k) if transposed
+                else _ct.geom_conv(b, h, wd, ci, co, k, stride, padding))
+        return _nhwc_out(_ct.conv_tc_nhwc(_nhwc(x), w, geom))
+    launch_stats["library"] += 1
+    wl = w.transpose(0, 1) if transposed else w
+    return torch.ops.aten.convolution(x, wl, None, *_conv_args(*cfg))
+
+
+def _nhwc_out(t: torch.Tensor) -> torch.Tensor:
+    """(B, H, W, C) kernel output -> logical (B, C, H, W), channels-last memory"""
+    return t.permute(0, 3, 1, 2)
+
+
+def _dgrad(g, w, x, cfg):
+    """gradient w.r.t. the input ``x`` (only its shape is used by the tcgen05 path)"""
+    stride, padding, transposed = cfg
+    x_shape = x.shape
+    co, ci, k, _ = w.shape
+    if _use_tc(g, w.shape, cfg, ci, co):
+        launch_stats["tc"] += 1
+        g, w = _cl(g), _cl(w)
+        b, _, h, wd = x_shape
+        if transposed:      # data gradient of the transposed conv = an ordinary stride-2 conv over g
+            geom = _ct.geom_conv(b, g.shape[2], g.shape[3], co, ci, k, 2, 0)
+        else:
+            geom = _ct.geom_conv_dgrad(b, h, wd, ci, co, k, stride, padding)
+        return _nhwc_out(_ct.conv_tc_nhwc(_nhwc(g), w, geom, transpose_weight=True))
+    launch_stats["library"] += 1
+    wl = w.transpose(0, 1) if transposed else w
+    gx, _, _ = torch.ops.aten.convolution_backward(g, x, wl, None, *_conv_args(*cfg), [True, False, False])
+    return gx
+
+
+def _wgrad(g, x, w, cfg):
+    """gradient w.r.t. the (Cout, Cin, k, k) weight ``w`` (only its shape / strides are used)"""
+    stride, padding, transposed = cfg
+    co, ci, k, _ = w.shape
+    if _use_tc(x, w.shape, cfg, co, ci) and _is_cl(w):
+        launch_stats["tc"] += 1
+        g, x = _cl(g), _cl(x)
+        b, _, h, wd = x.shape
+        geom = _ct.geom_wgrad(b, h, wd, ci, co, k, stride, padding, transposed)
+        return _ct.conv_wgrad_tc(_nhwc(g), _nhwc(x), geom, like=w)
+    launch_stats["library"] += 1
+    wl = w.transpose(0, 1) if transposed else w
+    _, gw, _ = torch.ops.aten.convolution_backward(g, x, wl, None, *_conv_args(*cfg), [False, True, False])
+    return gw.transpose(0, 1) if transposed else gw
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# autograd: first- and second-order structure
+# ---------------------------------------------------------------------------------------------------------------
+# R1 (train:462-493) and the path-length regulariser (train:546-589) differentiate THROUGH a backward pass.  Left to
+# autograd's generic double-backward formula, the weight-gradient term of a convolution is evaluated as a forward
+# convolution whose "filter" is a whole feature map; written out, every term of the second derivative is again one of
+# the three primitives with ordinary shapes:
+#     y  = fprop(x, w)          gx = dgrad(g, w)          gw = wgrad(g, x)
+#     d<ggx, gx>/dg = fprop(ggx, w)      d<ggx, gx>/dw = wgrad(g, ggx)
+#     d<ggw, gw>/dg = fprop(x, ggw)      d<ggw, gw>/dx = dgrad(g, ggw)
+# so the two Functions below call themselves / each other and stay differentiable to any order.  ``w`` is always the
+# layer's (Cout, Cin, k, k) weight, also for the transposed convolution (ModulatedConv2d's upsampling path).
 class _Conv(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, stride, padding, transposed):
         ctx.save_for_backward(x, w)
         ctx.cfg = (stride, padding, transposed)
-        return torch.ops.aten.convolution(x, w, None, *_conv_args(stride, padding, transposed))
+        return _fprop(x, w, ctx.cfg)
 
     @staticmethod
     def backward(ctx, g):
         x, w = ctx.saved_tensors
         need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        if not torch.is_grad_enabled():                    # plain backward (no create_graph): straight to the library
-            gx, gw, _ = torch.ops.aten.convolution_backward(g, x, w, None, *_conv_args(*ctx.cfg),
-                                                            [bool(need_x), bool(need_w), False])
+        if not torch.is_grad_enabled():                    # plain backward (no create_graph): straight to the kernels
+            gx = _dgrad(g, w, x, ctx.cfg) if need_x else None
+            gw = _wgrad(g, x, w, ctx.cfg) if need_w else None
             return gx, gw, None, None, None
         gx, gw = _ConvGrad.apply(g, x, w, need_x, need_w, *ctx.cfg)
         return gx, gw, None, None, None
@@ -67,8 +160,8 @@ class _ConvGrad(torch.autograd.Function):
     def forward(ctx, g, x, w, need_x, need_w, stride, padding, transposed):
         ctx.save_for_backward(g, x, w)
         ctx.cfg = (stride, padding, transposed)
-        gx, gw, _ = torch.ops.aten.convolution_backward(g, x, w, None, *_conv_args(stride, padding, transposed),
-                                                        [bool(need_x), bool(need_w), False])
+        gx = _dgrad(g, w, x, ctx.cfg) if need_x else None
+        gw = _wgrad(g, x, w, ctx.cfg) if need_w else None
         ctx.have = (bool(need_x), bool(need_w))
         return gx, gw                                      # None for a gradient that was not asked for
 
@@ -95,7 +188,8 @@ class _ConvGrad(torch.autograd.Function):
 
 
 def _lib_conv(x, w, stride: int = 1, padding: int = 0, transposed: bool = False):
-    """``F.conv2d`` / ``F.conv_transpose2d`` (groups 1, no bias) with the gradient structure above."""
+    """``F.conv2d(x, w)`` or, with ``transposed``, ``F.conv_transpose2d(x, w.transpose(0, 1))`` (groups 1, no bias;
+    ``w`` is (Cout, Cin, k, k) either way) with the gradient structure above."""
     return _Conv.apply(x, w, stride, padding, transposed)
 
 
@@ -120,11 +214,11 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
         if x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous():
             out = out.contiguous(memory_format=torch.channels_last)     # broadcasting does not keep the NHWC strides
         return out
-    if ci % 4 != 0 and ci > 4:
-        # D's final conv has 512 + 1 (minibatch-stddev) input channels; with a channel count that is not a multiple of
-        # 4 the library falls back to a SIMT convolution (0.7 ms for a 4x4 map in the round-1 profile).  Zero-padding
-        # the channel axis of input and weight keeps the result identical and the tensor-core kernels eligible.
-        extra = 4 - ci % 4
+    if ci % 32 != 0 and ci > 32:
+        # D's final conv has 512 + 1 (minibatch-stddev) input channels.  Zero-padding the channel axis of input and
+        # weight to the next multiple of 32 (one GEMM-K block) keeps the result identical and the layer on the tcgen05
+        # kernels (as a library conv an odd channel count fell back to a SIMT convolution: 0.7 ms for a 4x4 map).
+        extra = 32 - ci % 32
         x = F.pad(x, (0, 0, 0, 0, 0, extra))
         weight = F.pad(weight, (0, 0, 0, 0, 0, extra))
     out = _lib_conv(x, weight, stride, padding)
@@ -154,7 +248,7 @@ def modulated_conv2d(x: torch.Tensor, w: torch.Tensor, s: torch.Tensor, demod: O
         noise, noise_weight, bias, slope, act_scale = epilogue
         xm = _styled.modulate(x, s)
         if upsample:
-            out = blur(_lib_conv(xm, w.transpose(0, 1), 2, 0, True))
+            out = blur(_lib_conv(xm, w, 2, 0, True))
         else:
             out = _lib_conv(xm, w, 1, padding)
         if noise is None:
@@ -162,7 +256,7 @@ def modulated_conv2d(x: torch.Tensor, w: torch.Tensor, s: torch.Tensor, demod: O
         return _styled.styled_epilogue(out, demod, noise, noise_weight, bias, slope, act_scale)
     xm = x * s[:, :, None, None]
     if upsample:
-        out = _lib_conv(xm, w.transpose(0, 1), 2, 0, True)
+        out = _lib_conv(xm, w, 2, 0, True)
         out = blur(out)
     elif downsample:
         out = _lib_conv(blur(xm), w, 2, 0)

@@ -20,6 +20,12 @@
 //           coalesced NHWC stores (a warp writes 32 consecutive channels of one pixel = 128 B per instruction).
 // The transposed stride-2 convolution of the upsampling layers runs as four polyphase sub-convolutions (4/2/2/1 taps)
 // whose outputs interleave in the (2H+1)x(2W+1) result.
+//
+// The weight operand is described by strides (rick_conv_weight), so the SAME weight memory serves the forward pass
+// (GEMM-M = output channels, K-major rows: stride_k == 1) and the data gradient (GEMM-M = the layer's INPUT channels,
+// which are then the contiguous index: stride_m == 1, an MN-major operand staged as 32-channel blocks with the
+// 128B/32B-atom swizzle).  No transposed or re-packed copy of the weights exists anywhere.  Output-channel counts that
+// are not a multiple of 128 ride on TMA's out-of-bounds zero fill (the surplus accumulator rows are never stored).
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -63,6 +69,7 @@ struct ConvDev {
     int n_phases;
     PhaseDev phase[4];
     int cout_tiles, kblocks, tiles_per_group, total_tiles;   // sample group = nb samples; all phases share nb
+    int a_mn;                                                // weight operand is MN-major (data-gradient calls)
     float* out;
     float* out2;
     const float* demod;
@@ -106,7 +113,8 @@ template <bool ACT, bool DUAL, bool MULTI_B>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const int* __restrict__ offtab,
                                                const float* __restrict__ nztab, const short* __restrict__ btab,
                                                float* __restrict__ outp, long long out2_delta, const ConvDev& p, int co,
-                                               float bias, float alpha, float scale, float& dm, float& sn, int& cur_b) {
+                                               bool co_ok, float bias, float alpha, float scale, float& dm, float& sn,
+                                               int& cur_b) {
 #pragma unroll 8
     for (int j4 = 0; j4 < 32; j4 += 4) {
         const int4 oq = *reinterpret_cast<const int4*>(offtab + j4);
@@ -115,12 +123,12 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const in
         const float nzs[4] = {nq.x, nq.y, nq.z, nq.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int off = offs[k];                       // element offset of (pixel, channel 0), or -1
+            const int off = co_ok ? offs[k] : -1;          // element offset of (pixel, channel 0), or -1
             if (MULTI_B) {                                 // several samples per tile (small feature maps only)
                 const int b = btab[j4 + k];
                 if (off >= 0 && b != cur_b) {
                     cur_b = b;
-                    if (p.demod) dm = __ldg(p.demod + (size_t)b * p.cout + co);
+                    if (p.demod) dm = __ldg(p.demod + (size_t)b * p.cout + co) * tc::kTf32TruncationComp;
                     if (p.s_next) sn = __ldg(p.s_next + (size_t)b * p.cout + co);
                 }
             }
@@ -216,7 +224,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                         uint8_t* a_dst = smem + s * stage_bytes;
                         uint8_t* b_dst = a_dst + kABytes;
                         tc::mbar_arrive_expect_tx(&full_bar[s], kABytes + P.box_bytes);
-                        tc::tma_load_3d(a_dst, &tmap_w, &full_bar[s], kb * kBlockK, c.cout0, P.widx[tap]);
+                        if (!p.a_mn) {
+                            tc::tma_load_3d(a_dst, &tmap_w, &full_bar[s], kb * kBlockK, c.cout0, P.widx[tap]);
+                        } else {            // MN-major: four blocks of 32 M-channels x 32 K-rows (4 KB each)
+#pragma unroll
+                            for (int j = 0; j < kBlockM / 32; ++j)
+                                tc::tma_load_3d(a_dst + j * (kBlockK * 128), &tmap_w, &full_bar[s], c.cout0 + j * 32,
+                                                kb * kBlockK, P.widx[tap]);
+                        }
                         tc::tma_load_4d(b_dst, tmap_x, &full_bar[s], kb * kBlockK, gx, gy, c.b0);
                     }
                 }
@@ -229,7 +244,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_n) {
             const TileCoord c = decode_tile(p, t);
             const int n_kblocks = p.phase[c.phase].n_taps * p.kblocks;
-            const uint32_t idesc = tc::umma_idesc_tf32(kBlockM, p.phase[c.phase].n_mma);
+            const uint32_t idesc = tc::umma_idesc_tf32(kBlockM, p.phase[c.phase].n_mma, p.a_mn != 0, false);
             const uint32_t acc = tile_n & 1;
             tc::mbar_wait(&tmem_empty[acc], ((tile_n >> 1) & 1) ^ 1);
             tc::tc_fence_after_sync();
@@ -240,12 +255,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                 tc::tc_fence_after_sync();
                 if (tc::elect_one()) {
                     const uint32_t a_addr = tc::smem_u32(smem + s * stage_bytes);
-                    const uint64_t a_desc = tc::umma_desc_k_sw128(a_addr);
                     const uint64_t b_desc = tc::umma_desc_k_sw128(a_addr + kABytes);
+                    if (!p.a_mn) {
+                        const uint64_t a_desc = tc::umma_desc_k_sw128(a_addr);
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 8; ++k) {
-                        // advance 8 tf32 = 32 bytes along K inside the swizzled row: +2 in the (addr >> 4) field
-                        tc::umma_tf32_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                        for (int k = 0; k < kBlockK / 8; ++k) {
+                            // advance 8 tf32 = 32 bytes along K inside the swizzled row: +2 in the (addr >> 4) field
+                            tc::umma_tf32_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 8; ++k) {
+                            // MN-major A: 8 K-rows = 1024 B further down each 32-channel block
+                            const uint64_t a_desc = tc::umma_desc_mn_sw128_32b(a_addr + k * 1024, kBlockK * 128);
+                            tc::umma_tf32_ss(d_tmem, a_desc, b_desc + 2 * k, idesc, (kb | k) != 0);
+                        }
                     }
                     tc::umma_commit(&empty_bar[s]);                       // smem stage reusable once these MMAs retire
                     if (kb == n_kblocks - 1) tc::umma_commit(&tmem_full[acc]);   // accumulator complete
@@ -291,10 +315,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
 
-            const int co = c.cout0 + quarter * 32 + lane;
+            const bool co_ok = c.cout0 + quarter * 32 + lane < p.cout;     // cout % 128 != 0: surplus rows are zero, unused
+            const int co = co_ok ? c.cout0 + quarter * 32 + lane : 0;
             const float bias = p.bias ? __ldg(p.bias + co) : 0.f;
             int cur_b = c.b0 < p.batch ? c.b0 : p.batch - 1;
-            float dm = p.demod ? __ldg(p.demod + (size_t)cur_b * p.cout + co) : 1.f;
+            float dm = (p.demod ? __ldg(p.demod + (size_t)cur_b * p.cout + co) : 1.f) * tc::kTf32TruncationComp;
             float sn = p.s_next ? __ldg(p.s_next + (size_t)cur_b * p.cout + co) : 1.f;
             tc::mbar_wait(&tmem_full[acc], (tile_n >> 1) & 1);
             tc::tc_fence_after_sync();
@@ -306,11 +331,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                 tc::tmem_ld_32x32b_x32(taddr + n0, v);
                 tc::tmem_ld_wait();
                 if (P.nb > 1)
-                    epilogue_chunk<ACT, DUAL, true>(v, pixtab + n0, nztab + n0, btab + n0, outp, out2_delta, p, co, bias,
-                                                    alpha, scale, dm, sn, cur_b);
+                    epilogue_chunk<ACT, DUAL, true>(v, pixtab + n0, nztab + n0, btab + n0, outp, out2_delta, p, co, co_ok,
+                                                    bias, alpha, scale, dm, sn, cur_b);
                 else
-                    epilogue_chunk<ACT, DUAL, false>(v, pixtab + n0, nztab + n0, btab + n0, outp, out2_delta, p, co, bias,
-                                                     alpha, scale, dm, sn, cur_b);
+                    epilogue_chunk<ACT, DUAL, false>(v, pixtab + n0, nztab + n0, btab + n0, outp, out2_delta, p, co, co_ok,
+                                                     bias, alpha, scale, dm, sn, cur_b);
             }
             tc::tc_fence_before_sync();
             __syncwarp();
@@ -331,12 +356,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
 
 extern "C" int rick_conv_tc(void* out, const void* xm, const void* wt, const rick_conv_geom* g,
                             const rick_conv_epilogue* e, rick_stream_t stream) {
+    if (!g) return RICK_ERR_INVALID_ARGUMENT;
+    // packed (n_weight_taps, cout, cin) weights: one K-major matrix per tap
+    rick_conv_weight w{wt, (int64_t)g->cin, 1, (int64_t)g->cin * g->cout};
+    return rick_conv_tc_w(out, xm, &w, g, e, stream);
+}
+
+extern "C" int rick_conv_tc_w(void* out, const void* xm, const rick_conv_weight* wd, const rick_conv_geom* g,
+                              const rick_conv_epilogue* e, rick_stream_t stream) {
     using namespace rick;
-    if (!out || !xm || !wt || !g) return RICK_ERR_INVALID_ARGUMENT;
+    if (!out || !xm || !wd || !wd->ptr || !g) return RICK_ERR_INVALID_ARGUMENT;
+    const void* wt = wd->ptr;
     if (g->batch < 1 || g->in_h < 1 || g->in_w < 1 || g->out_h < 1 || g->out_w < 1) return RICK_ERR_INVALID_ARGUMENT;
     if (g->n_phases < 1 || g->n_phases > 4 || g->n_weight_taps < 1) return RICK_ERR_INVALID_ARGUMENT;
-    if (g->cout % kBlockM != 0 || g->cin % kBlockK != 0) return RICK_ERR_UNSUPPORTED;
+    if (g->cout % 32 != 0 || g->cin % kBlockK != 0) return RICK_ERR_UNSUPPORTED;
     if (g->in_stride < 1 || g->in_stride > 2 || g->out_stride < 1 || g->out_stride > 2) return RICK_ERR_UNSUPPORTED;
+    // exactly one of the two channel indices of the weight must be contiguous; every other stride a multiple of 16 B
+    const bool a_mn = wd->stride_m == 1 && wd->stride_k != 1;
+    if (!a_mn && wd->stride_k != 1) return RICK_ERR_UNSUPPORTED;
+    if ((a_mn ? wd->stride_k : wd->stride_m) % 4 != 0 || (g->n_weight_taps > 1 && wd->stride_tap % 4 != 0) ||
+        wd->stride_m < 1 || wd->stride_k < 1 || wd->stride_tap < 0)
+        return RICK_ERR_ALIGNMENT;
     if (!aligned_to(out, 16) || !aligned_to(xm, 16) || !aligned_to(wt, 16)) return RICK_ERR_ALIGNMENT;
     if ((long long)g->batch * g->out_h * g->out_w * g->cout > 0x7fffffffLL) return RICK_ERR_OVERFLOW;   // 32-bit offsets
     EncodeTiledFn encode = get_encode_tiled();
@@ -379,7 +419,8 @@ extern "C" int rick_conv_tc(void* out, const void* xm, const void* wt, const ric
     ConvDev p{};
     p.batch = g->batch, p.cout = g->cout, p.out_h = g->out_h, p.out_w = g->out_w;
     p.in_stride = g->in_stride, p.out_stride = g->out_stride, p.n_phases = g->n_phases;
-    p.cout_tiles = g->cout / kBlockM, p.kblocks = g->cin / kBlockK;
+    p.cout_tiles = (int)ceil_div(g->cout, kBlockM), p.kblocks = g->cin / kBlockK;
+    p.a_mn = a_mn ? 1 : 0;
     int nb_common = 1 << 30;
     int ptw[4], pth[4];
     for (int i = 0; i < g->n_phases; ++i) {
@@ -426,14 +467,26 @@ extern "C" int rick_conv_tc(void* out, const void* xm, const void* wt, const ric
     // ---- tensor maps ----
     CUtensorMap tmap_w, tmap_x[4];
     {
-        cuuint64_t dims[3] = {(cuuint64_t)g->cin, (cuuint64_t)g->cout, (cuuint64_t)g->n_weight_taps};
-        cuuint64_t strides[2] = {(cuuint64_t)g->cin * 4, (cuuint64_t)g->cin * g->cout * 4};
-        cuuint32_t box[3] = {kBlockK, kBlockM, 1};
+        // a single-tap weight may come with any tap stride (it is never used): give the degenerate dimension a legal one
+        const cuuint64_t tap_stride = g->n_weight_taps > 1 ? (cuuint64_t)wd->stride_tap * 4 : 16;
         cuuint32_t estr[3] = {1, 1, 1};
-        if (encode(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(wt), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-            return RICK_ERR_INVALID_ARGUMENT;
+        CUresult rc;
+        if (!a_mn) {    // K-major: rows of cin (contiguous), one row per output channel
+            cuuint64_t dims[3] = {(cuuint64_t)g->cin, (cuuint64_t)g->cout, (cuuint64_t)g->n_weight_taps};
+            cuuint64_t strides[2] = {(cuuint64_t)wd->stride_m * 4, tap_stride};
+            cuuint32_t box[3] = {kBlockK, kBlockM, 1};
+            rc = encode(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(wt), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        } else {        // MN-major: the GEMM-M channel (cout of THIS call) is contiguous, rows run over GEMM-K (cin)
+            cuuint64_t dims[3] = {(cuuint64_t)g->cout, (cuuint64_t)g->cin, (cuuint64_t)g->n_weight_taps};
+            cuuint64_t strides[2] = {(cuuint64_t)wd->stride_k * 4, tap_stride};
+            cuuint32_t box[3] = {32, kBlockK, 1};
+            rc = encode(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(wt), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
+        if (rc != CUDA_SUCCESS) return RICK_ERR_INVALID_ARGUMENT;
     }
     for (int i = 0; i < 4; ++i) {
         const PhaseDev& P = p.phase[i < g->n_phases ? i : 0];

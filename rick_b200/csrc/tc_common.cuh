@@ -140,13 +140,40 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr, uint32
     return d;
 }
 
-// Instruction descriptor, kind::tf32, fp32 accumulate, both operands K-major:
-//   [4,6) D format (1 = f32)  [7,10) A format (2 = tf32)  [10,13) B format (2 = tf32)  [15] A major  [16] B major
-//   [17,23) N >> 3            [24,29) M >> 4
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
-           (static_cast<uint32_t>(m >> 4) << 24);
+// Shared-memory matrix descriptor for an MN-major fp32/tf32 operand tile (the GEMM-M or -N index is the contiguous one).
+// 32-bit MN-major operands have exactly one swizzled layout: "128B swizzle with 32B atomicity" (layout type 1), which is
+// what a TMA box with inner extent 32 floats and CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B produces.  The tile is a sequence of
+// blocks of 32 MN-elements (128 B rows) x K rows; inside a block rows are 128 B apart and form 4-row (512 B) swizzle
+// groups.  One MMA (K = 8) reads rows [0, 8) from the start address:
+//   [16,30) leading byte offset >> 4 = distance between consecutive 32-element MN blocks
+//   [32,46) stride  byte offset >> 4 = distance between consecutive 4-row groups (512 B for densely stored rows)
+// Advancing K by 8 rows = start address + 1024 B.  Verified on hardware by scripts/probe_mnmajor.cu (round 2).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128_32b(uint32_t smem_addr, uint32_t block_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3ffff) >> 4);
+    d |= static_cast<uint64_t>((block_bytes >> 4) & 0x3fff) << 16;
+    d |= static_cast<uint64_t>(512 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(1) << 61;
+    return d;
 }
+
+// Instruction descriptor, kind::tf32, fp32 accumulate:
+//   [4,6) D format (1 = f32)  [7,10) A format (2 = tf32)  [10,13) B format (2 = tf32)
+//   [15] A major (0 = K-major, 1 = MN-major)  [16] B major  [17,23) N >> 3  [24,29) M >> 4
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n, bool a_mn = false, bool b_mn = false) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u) |
+           (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// tcgen05.mma.kind::tf32 consumes the upper 19 bits of each fp32 operand: the 13 low mantissa bits are TRUNCATED, not
+// rounded.  Every operand therefore shrinks by E[(ulp/2) / |x|] = 0.5 * 2^-10 * E[1/m] (mantissa m log-uniform in [1, 2):
+// E[1/m] = 1 / (2 ln 2)) = 3.522e-4, and a product of two truncated operands by 7.044e-4 -- a systematic gain error that
+// compounds through the 13 convolutions of the generator.  Scaling the accumulator by this constant in the epilogue
+// removes the bias; the remainder is zero-mean with the variance of round-to-nearest.  Measured on the 256 px golden
+// image (scripts/exp_tf32_rounding.py): max-abs error 6.4e-2 as is, 8.1e-3 with both operands pre-rounded to nearest,
+// 6.5e-3 with this compensation (the cuDNN TF32 path: 7.7e-3).
+constexpr float kTf32TruncationComp = 1.0007044f;
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread on behalf of the CTA
 __device__ __forceinline__ void umma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,

@@ -13,6 +13,7 @@ from typing import Dict, Iterable, List, Optional
 import torch
 
 from . import _lib
+from .rick import filter_major
 
 
 def _stream() -> int:
@@ -80,12 +81,12 @@ class FusedMaskedAdam:
             e = self.ema_named[name] if (ema and self.ema_named is not None) else None
             if g is None and e is None:
                 continue
-            if not p.is_contiguous() and not (p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last)):
+            st = state.get(name) if g is not None else None
+            if not filter_major(p, st.numel() if st is not None else 1):
                 raise RuntimeError(f"FusedMaskedAdam: {name} is not stored filter-major")
             for other, what in ((g, "gradient"), (e, "EMA copy")):
                 if other is not None and not _same_layout(p, other):
                     raise RuntimeError(f"FusedMaskedAdam: {what} of {name} does not share the parameter's memory layout")
-            st = state.get(name) if g is not None else None
             r = st.numel() if st is not None else 1
             if g is not None:
                 stepped[self._slot[id(p)]] = True

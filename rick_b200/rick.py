@@ -33,6 +33,24 @@ def _stream() -> int:
 
 # ------------------------------------------------------------------------------------------------ accumulation
 
+def filter_major(t: torch.Tensor, rows: int = 1) -> bool:
+    """True when ``t`` is stored densely (a permutation of a contiguous block) with its filter dimension outermost, so
+    that filter r occupies elements [r * inner, (r + 1) * inner) of its storage -- what the per-filter kernels assume.
+    Holds for contiguous tensors, channels-last 4-D weights and the (1, Cout, Cin, k, k) modulated-conv weights kept
+    as [Cout][k][k][Cin].  The filter dimension is dim 1 for 5-D tensors (train:526-537), else dim 0."""
+    sizes, strides = list(t.shape), list(t.stride())
+    dims = sorted((d for d in range(t.dim()) if sizes[d] > 1), key=lambda d: -strides[d])
+    expect = t.numel()
+    for d in dims:                                   # dense: each stride is the product of the sizes inside it
+        expect //= sizes[d]
+        if strides[d] != expect:
+            return False
+    if rows <= 1 or not dims:
+        return True
+    fd = 1 if t.dim() == 5 else 0
+    return sizes[fd] == rows and dims[0] == fd
+
+
 class FisherAccumulator:
     """Sum of squared gradients per parameter (train:252-263), kept on the device in float32."""
 
@@ -195,12 +213,11 @@ class FilterMasks:
         for name, st in self.state.items():
             p = named_params[name]
             g = p.grad
-            for t in (p, g):
-                # rows (= filters, dim 0) must be the outermost, dense blocks of memory: true for contiguous and for
-                # channels-last 4-D tensors alike
-                if t is not None and not (t.is_contiguous() or t.is_contiguous(memory_format=torch.channels_last)):
-                    raise RuntimeError(f"FilterMasks.apply: {name} (or its gradient) is not stored filter-major")
             r = st.numel()
+            for t in (p, g):
+                # rows (= filters) must be the outermost, dense blocks of memory
+                if t is not None and not filter_major(t, r):
+                    raise RuntimeError(f"FilterMasks.apply: {name} (or its gradient) is not stored filter-major")
             params.append(p.data_ptr())
             grads.append(g.data_ptr() if g is not None else None)
             states.append(st.data_ptr())

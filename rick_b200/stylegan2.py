@@ -237,7 +237,12 @@ class ModulatedConv2d(nn.Module):
             self.blur = Blur(blur_kernel, pad=_fir_pads(len(blur_kernel), 2, kernel_size, "conv_down"))
         self.scale = 1 / math.sqrt(in_channel * kernel_size ** 2)
         self.padding = kernel_size // 2
-        self.weight = nn.Parameter(torch.randn(1, out_channel, in_channel, kernel_size, kernel_size))
+        w = torch.randn(1, out_channel, in_channel, kernel_size, kernel_size)
+        if _CHANNELS_LAST:
+            # same shape / state_dict entry as the reference; MEMORY is [Cout][k][k][Cin] so that the tcgen05 kernels
+            # read it in place as a K-major (forward) or MN-major (data gradient) operand and write its gradient there
+            w = w.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
+        self.weight = nn.Parameter(w)
         self.modulation = EqualLinear(style_dim, in_channel, bias_init=1)
         self.demodulate = demodulate
 
@@ -251,7 +256,7 @@ class ModulatedConv2d(nn.Module):
         s = self.modulation(style)                                   # (B, Cin)
         # conv(x * s, scale * W) == conv(x * (scale * s), W): the equalised-lr scale rides on the (B, Cin) style, so
         # the 2.4 M-float weight is not rescaled (one multiply kernel + one in backward per layer and call)
-        w = self.weight[0]                                           # (Cout, Cin, k, k), shared by the batch
+        w = self.weight.squeeze(0)                                   # (Cout, Cin, k, k), shared by the batch
         demod = None
         if self.demodulate:
             wsq = w.pow(2).sum([2, 3])                               # (Cout, Cin)

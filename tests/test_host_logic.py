@@ -358,3 +358,99 @@ def test_d_pair_grouping_matches_two_calls(batch, cap):
     got_f, got_r = d_pair(d, fake, real)
     torch.testing.assert_close(got_f, want_f)
     torch.testing.assert_close(got_r, want_r)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# geometry builders of the tcgen05 convolution (rick_b200.conv_tc): interpreted on the CPU exactly as the kernels read
+# them (include/rick_b200.h) and compared with torch's convolution / its gradients
+# ---------------------------------------------------------------------------------------------------------------
+def _interp_conv(x, w, geom, transpose_weight):
+    """rick_conv_tc_w semantics: x (B,H,W,K) NHWC, w (Cout,Cin,k,k); returns (B,OH,OW,M)."""
+    import torch
+    B = geom.batch
+    out = torch.zeros(B, geom.out_h, geom.out_w, geom.cout, dtype=torch.float64)
+    k = w.shape[-1]
+    for i in range(geom.n_phases):
+        ph = geom.phase[i]
+        for t in range(ph.n_taps):
+            ky, kx = divmod(ph.widx[t], k)
+            wm = w[:, :, ky, kx].double()                     # (Cout, Cin)
+            op = wm.t() if transpose_weight else wm           # (M, K)
+            for m in range(ph.rows):
+                iy = m * geom.in_stride + ph.dy[t]
+                if not 0 <= iy < geom.in_h:
+                    continue
+                for n in range(ph.cols):
+                    ix = n * geom.in_stride + ph.dx[t]
+                    if not 0 <= ix < geom.in_w:
+                        continue
+                    out[:, m * geom.out_stride + ph.out_y0, n * geom.out_stride + ph.out_x0] += x[:, iy, ix].double() @ op.t()
+    return out
+
+
+def _interp_wgrad(g, x, geom, k):
+    import torch
+    dw = torch.zeros(geom.cout, geom.cin, k, k, dtype=torch.float64)
+    for t in range(geom.n_taps):
+        ky, kx = divmod(t, k)
+        for m in range(geom.rows):
+            gy, xy = m * geom.g_stride + geom.gy[t], m * geom.x_stride + geom.xy[t]
+            if not (0 <= gy < geom.g_h and 0 <= xy < geom.x_h):
+                continue
+            for n in range(geom.cols):
+                gx, xx = n * geom.g_stride + geom.gx[t], n * geom.x_stride + geom.xx[t]
+                if not (0 <= gx < geom.g_w and 0 <= xx < geom.x_w):
+                    continue
+                dw[:, :, ky, kx] += g[:, gy, gx].double().t() @ x[:, xy, xx].double()
+    return dw
+
+
+@pytest.mark.parametrize("k,stride,pad,h,w", [(3, 1, 1, 6, 5), (1, 1, 0, 4, 4), (3, 2, 0, 9, 9), (3, 2, 0, 7, 11),
+                                              (1, 2, 0, 7, 7), (3, 2, 1, 8, 8), (3, 2, 0, 8, 10)])
+def test_conv_geometries_match_torch_conv_and_gradients(k, stride, pad, h, w):
+    import torch
+    from torch.nn import functional as F
+    from rick_b200 import conv_tc as ct
+    g = torch.Generator().manual_seed(k * 100 + stride * 10 + h)
+    B, cin, cout = 2, 3, 4
+    x = torch.randn(B, cin, h, w, generator=g, dtype=torch.float64, requires_grad=True)
+    wt = torch.randn(cout, cin, k, k, generator=g, dtype=torch.float64, requires_grad=True)
+    y = F.conv2d(x, wt, stride=stride, padding=pad)
+    go = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    gx, gw = torch.autograd.grad(y, [x, wt], go)
+    nhwc = lambda t: t.detach().permute(0, 2, 3, 1).contiguous()
+    # forward
+    got = _interp_conv(nhwc(x), wt.detach(), ct.geom_conv(B, h, w, cin, cout, k, stride, pad), False)
+    torch.testing.assert_close(got, nhwc(y))
+    # data gradient: the transposed problem over the same weight memory
+    gd = ct.geom_conv_dgrad(B, h, w, cin, cout, k, stride, pad)
+    assert (gd.in_h, gd.in_w, gd.out_h, gd.out_w, gd.cin, gd.cout) == (y.shape[2], y.shape[3], h, w, cout, cin)
+    got = _interp_conv(nhwc(go), wt.detach(), gd, True)
+    torch.testing.assert_close(got, nhwc(gx))
+    if k == 1 and stride == 2:
+        assert ct._covers_partially(gd)              # odd pixels receive no gradient and no phase writes them: pre-zeroed
+    # weight gradient
+    got = _interp_wgrad(nhwc(go), nhwc(x), ct.geom_wgrad(B, h, w, cin, cout, k, stride, pad), k)
+    torch.testing.assert_close(got, gw)
+
+
+def test_transposed_conv_geometries_match_torch():
+    import torch
+    from torch.nn import functional as F
+    from rick_b200 import conv_tc as ct
+    g = torch.Generator().manual_seed(3)
+    B, cin, cout, h, w, k = 2, 3, 4, 5, 6, 3
+    x = torch.randn(B, cin, h, w, generator=g, dtype=torch.float64, requires_grad=True)
+    wt = torch.randn(cout, cin, k, k, generator=g, dtype=torch.float64, requires_grad=True)     # ModulatedConv2d's (Cout, Cin)
+    y = F.conv_transpose2d(x, wt.transpose(0, 1), stride=2)                                      # model_probe_tune.py:265
+    go = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    gx, gw = torch.autograd.grad(y, [x, wt], go)
+    nhwc = lambda t: t.detach().permute(0, 2, 3, 1).contiguous()
+    got = _interp_conv(nhwc(x), wt.detach(), ct.geom_conv_transpose_s2(B, h, w, cin, cout), False)
+    torch.testing.assert_close(got, nhwc(y))
+    # its data gradient is an ordinary stride-2 convolution of g with the weight read transposed (M = Cin, K = Cout)
+    gd = ct.geom_conv(B, 2 * h + 1, 2 * w + 1, cout, cin, k, 2, 0)
+    got = _interp_conv(nhwc(go), wt.detach(), gd, True)
+    torch.testing.assert_close(got, nhwc(gx))
+    got = _interp_wgrad(nhwc(go), nhwc(x), ct.geom_wgrad(B, h, w, cin, cout, k, 2, 0, transposed=True), k)
+    torch.testing.assert_close(got, gw)
