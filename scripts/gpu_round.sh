@@ -1,40 +1,34 @@
 #!/bin/bash
 # One gpurun call.  Every step has its own short timeout and writes its log unbuffered, so a hung kernel costs
-# minutes, not the whole call.   usage: gpu_round.sh [tests] [bench] [ncu]
+# minutes, not the whole call.   usage: gpu_round.sh [tests] [bench] [ncu] [ncuops] [smoke]
 export PYTHONUNBUFFERED=1
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 echo "cores: $(nproc)" >> gpurun_out/gpu.txt
-want() { [[ " $* " == *" $STEP "* ]]; }
 for STEP in "$@"; do
 case $STEP in
-debug)
-  timeout 150 python -u scripts/debug_conv_tc.py > gpurun_out/debug_conv_tc.log 2>&1; echo "debug_conv_tc rc=$?"
-  tail -25 gpurun_out/debug_conv_tc.log ;;
 tests)
-  for f in ${TEST_FILES:-tests/test_ops_gpu.py tests/test_rick_gpu.py tests/test_conv_tc_gpu.py tests/test_model_gpu.py tests/test_adapt_gpu.py}; do
+  for f in ${TEST_FILES:-tests/test_ops_gpu.py tests/test_rick_gpu.py tests/test_conv_tc_gpu.py tests/test_conv_train_gpu.py tests/test_model_gpu.py tests/test_adapt_gpu.py}; do
     log=gpurun_out/pytest_$(basename $f .py).log
-    timeout ${TEST_TIMEOUT:-420} python -u -m pytest $f -m gpu -q -rA -x --timeout=200 -p no:cacheprovider > $log 2>&1
+    timeout ${TEST_TIMEOUT:-420} python -u -m pytest $f -m gpu -q -rA --timeout=300 -p no:cacheprovider ${PYTEST_ARGS} > $log 2>&1
     echo "=== $f rc=$? : $(tail -1 $log)"
-    grep -E "^(FAILED|ERROR)" $log | head -8
+    grep -E "^(FAILED|ERROR)" $log | head -12
   done ;;
+smoke)
+  timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 ;;
 bench)
   timeout 600 python -u bench.py --steps ${BENCH_STEPS:-20} --warmup 3 ${BENCH_ARGS} > gpurun_out/bench${BENCH_TAG}.json 2> gpurun_out/bench${BENCH_TAG}.err
-  echo "bench rc=$?"; tail -c 4500 gpurun_out/bench${BENCH_TAG}.json; tail -5 gpurun_out/bench${BENCH_TAG}.err ;;
+  echo "bench rc=$?"; tail -c 6000 gpurun_out/bench${BENCH_TAG}.json; tail -5 gpurun_out/bench${BENCH_TAG}.err ;;
 ncu)
   timeout 560 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 2600 --csv \
       --log-file gpurun_out/launches${NCU_TAG}.csv \
       python -u bench.py --steps 1 --warmup 3 --no-cpu-baseline --quick --cuda-profiler ${NCU_BENCH_ARGS:---mode eager} \
       > gpurun_out/ncu_bench${NCU_TAG}.log 2>&1
-  echo "ncu launches rc=$?"
-  timeout 300 ncu --set full --clock-control none --import-source on \
-      -k regex:'upfirdn2d|bias_act_vec|bias_act_bwd|blur_nhwc|conv_tc|adam_mask_ema' -s 9 -c 9 \
-      -o gpurun_out/prof_ops python -u scripts/prof_ops.py > gpurun_out/ncu_ops.log 2>&1
-  echo "ncu ops rc=$?" ;;
+  echo "ncu launches rc=$?" ;;
 ncuops)
   timeout 300 ncu --set full --clock-control none --import-source on \
-      -k regex:'upfirdn2d|bias_act_vec|bias_act_bwd|blur_nhwc|conv_tc|adam_mask_ema' -s 9 -c 9 \
-      -o gpurun_out/prof_ops python -u scripts/prof_ops.py > gpurun_out/ncu_ops.log 2>&1
+      -k regex:${NCU_KERNELS:-'upfirdn2d|bias_act_vec|bias_act_bwd|blur_nhwc|conv_tc|conv_wgrad|adam_mask_ema'} -s ${NCU_SKIP:-9} -c ${NCU_COUNT:-9} \
+      -o gpurun_out/prof_ops${NCU_TAG} python -u ${NCU_SCRIPT:-scripts/prof_ops.py} > gpurun_out/ncu_ops${NCU_TAG}.log 2>&1
   echo "ncu ops rc=$?" ;;
 esac
 done
