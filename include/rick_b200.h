@@ -221,14 +221,23 @@ RICK_API int rick_conv_tc(void* out, const void* xm, const void* wt, const rick_
  *                  layer's Cin, geom->cin its Cout, the taps are mirrored -- over the SAME memory: stride_m = 1,
  *                  stride_k = k*k*Cin, stride_tap = Cin.  stride_m == 1 makes the weight an MN-major UMMA operand.
  * Element (m, k, tap) of the operand is ptr[m*stride_m + k*stride_k + widx*stride_tap].  Exactly one of stride_m /
- * stride_k must be 1, the others multiples of 4 elements.  geom->cout % 32 == 0, geom->cin % 32 == 0. */
+ * stride_k must be 1, the others multiples of 4 elements.  geom->cout % 32 == 0, geom->cin % 32 == 0.
+ *
+ * Split-K.  When the convolution has fewer output tiles than the GPU has SMs (the 4x4 ... 32x32 feature maps of the
+ * batch-2 adaptation loop: a 512 -> 512 layer on a 4x4 map is 4 tiles, each streaming 2.4 MB of weights), the
+ * (tap, input-channel-block) iterations of every tile are divided over several CTAs; their partial sums go to
+ * `workspace` and a second kernel adds them in a fixed order (deterministic) and applies the epilogue.
+ * rick_conv_tc_workspace(geom) returns the bytes that takes (0: no split for this geometry; negative: unsupported).
+ * With workspace == NULL or workspace_bytes too small the call runs unsplit. */
 typedef struct rick_conv_weight {
     const void* ptr;
     int64_t stride_m, stride_k, stride_tap;
 } rick_conv_weight;
 
+RICK_API int64_t rick_conv_tc_workspace(const rick_conv_geom* geom);
 RICK_API int rick_conv_tc_w(void* out, const void* xm, const rick_conv_weight* weight, const rick_conv_geom* geom,
-                            const rick_conv_epilogue* epilogue, rick_stream_t stream);
+                            const rick_conv_epilogue* epilogue, void* workspace, int64_t workspace_bytes,
+                            rick_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------- tcgen05 weight gradient
  * dW of the convolutions above (in the reference: autograd's cuDNN wgrad behind model_probe_tune.py:122-128, 265, 274,

@@ -43,7 +43,8 @@ class WgradGeom(ctypes.Structure):
 _lib._OPTIONAL["rick_conv_tc"] = (c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(ConvGeom),
                                           ctypes.POINTER(ConvEpilogue), c_void_p])
 _lib._OPTIONAL["rick_conv_tc_w"] = (c_int, [c_void_p, c_void_p, ctypes.POINTER(ConvWeight), ctypes.POINTER(ConvGeom),
-                                            ctypes.POINTER(ConvEpilogue), c_void_p])
+                                            ctypes.POINTER(ConvEpilogue), c_void_p, c_int64, c_void_p])
+_lib._OPTIONAL["rick_conv_tc_workspace"] = (c_int64, [ctypes.POINTER(ConvGeom)])
 _lib._OPTIONAL["rick_conv_wgrad_workspace"] = (c_int64, [ctypes.POINTER(WgradGeom)])
 _lib._OPTIONAL["rick_conv_wgrad_tc"] = (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                                                 ctypes.POINTER(WgradGeom), c_void_p, c_float, c_void_p])
@@ -53,6 +54,9 @@ _lib._OPTIONAL["rick_blur_nhwc"] = (c_int, [c_void_p, c_void_p, c_void_p, c_int,
                                             ctypes.POINTER(ConvEpilogue), c_void_p])
 _lib._OPTIONAL["rick_to_rgb_nhwc"] = (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                               c_int, c_void_p])
+
+
+SPLIT_K = True      # divide the K loop of small-map convolutions over idle SMs (tests switch it off to compare)
 
 
 def supported(cin: int, cout: int) -> bool:
@@ -263,9 +267,12 @@ def conv_tc_nhwc(xm: torch.Tensor, wt: torch.Tensor, geom: ConvGeom, demod=None,
     out2 = torch.empty_like(out) if want_out2 else None
     ep = ConvEpilogue(_ptr(demod), _ptr(noise), _ptr(noise_weight), _ptr(bias), _ptr(s_next), _ptr(out2), int(act),
                       float(alpha), float(scale))
+    lib = _lib.lib()
+    ws_bytes = int(lib.rick_conv_tc_workspace(ctypes.byref(geom))) if SPLIT_K else 0
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xm.device) if ws_bytes > 0 else None     # split-K partial sums
     with torch.cuda.device(xm.device):
-        st = _lib.lib().rick_conv_tc_w(out.data_ptr(), xm.data_ptr(), ctypes.byref(wd), ctypes.byref(geom),
-                                       ctypes.byref(ep), torch.cuda.current_stream().cuda_stream)
+        st = lib.rick_conv_tc_w(out.data_ptr(), xm.data_ptr(), ctypes.byref(wd), ctypes.byref(geom), ctypes.byref(ep),
+                                _ptr(ws), max(ws_bytes, 0), torch.cuda.current_stream().cuda_stream)
     _lib.check(st, "rick_conv_tc_w")
     return (out, out2) if want_out2 else out
 

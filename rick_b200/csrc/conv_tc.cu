@@ -70,6 +70,11 @@ struct ConvDev {
     PhaseDev phase[4];
     int cout_tiles, kblocks, tiles_per_group, total_tiles;   // sample group = nb samples; all phases share nb
     int a_mn;                                                // weight operand is MN-major (data-gradient calls)
+    // split-K (small feature maps: fewer output tiles than SMs): every tile's (tap, channel-block) iterations are cut
+    // into ksplit ranges, one CTA-visit each; raw partial sums go to plane `range` of the workspace (out points at it,
+    // planes split_plane elements apart) and conv_fold_kernel adds them in a fixed order and applies the epilogue
+    int ksplit;
+    long long split_plane;
     float* out;
     float* out2;
     const float* demod;
@@ -195,14 +200,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         // ===================================================== TMA producer
         if (lane == 0) {
             uint32_t it = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            for (int vt = blockIdx.x; vt < p.total_tiles * p.ksplit; vt += gridDim.x) {
+                const int t = vt / p.ksplit, sp = vt - t * p.ksplit;
                 const TileCoord c = decode_tile(p, t);
                 const PhaseDev& P = p.phase[c.phase];
                 const CUtensorMap* tmap_x = c.phase == 0 ? &tmap_x0 : (c.phase == 1 ? &tmap_x1 : (c.phase == 2 ? &tmap_x2 : &tmap_x3));
                 // Shallow-K layers (Cin <= 256) finish a tile in ~10 us, too little for a 4-stage ring to cover the DRAM
                 // latency of rows that no tile has touched yet: pull the NEXT tile's activation rows into L2 now (one
                 // box per distinct dy; the dx-shifted boxes overlap it).
-                if (p.kblocks <= 8 && t + (int)gridDim.x < p.total_tiles) {
+                if (p.ksplit == 1 && p.kblocks <= 8 && t + (int)gridDim.x < p.total_tiles) {
                     const TileCoord cn = decode_tile(p, t + gridDim.x);
                     const PhaseDev& Pn = p.phase[cn.phase];
                     const CUtensorMap* tmap_n = cn.phase == 0 ? &tmap_x0 : (cn.phase == 1 ? &tmap_x1 : (cn.phase == 2 ? &tmap_x2 : &tmap_x3));
@@ -215,25 +221,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                                                    cn.y0 * p.in_stride + Pn.dy[tap], cn.b0);
                     }
                 }
-                for (int tap = 0; tap < P.n_taps; ++tap) {
+                const int n_k = P.n_taps * p.kblocks;
+                const int k0 = n_k * sp / p.ksplit, k1 = n_k * (sp + 1) / p.ksplit;
+                int tap = k0 / p.kblocks, kb = k0 - tap * p.kblocks;
+                for (int kk = k0; kk < k1; ++kk, ++it) {
                     const int gx = c.x0 * p.in_stride + P.dx[tap];
                     const int gy = c.y0 * p.in_stride + P.dy[tap];
-                    for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
-                        const int s = it % kStages;
-                        tc::mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
-                        uint8_t* a_dst = smem + s * stage_bytes;
-                        uint8_t* b_dst = a_dst + kABytes;
-                        tc::mbar_arrive_expect_tx(&full_bar[s], kABytes + P.box_bytes);
-                        if (!p.a_mn) {
-                            tc::tma_load_3d(a_dst, &tmap_w, &full_bar[s], kb * kBlockK, c.cout0, P.widx[tap]);
-                        } else {            // MN-major: four blocks of 32 M-channels x 32 K-rows (4 KB each)
-#pragma unroll
-                            for (int j = 0; j < kBlockM / 32; ++j)
-                                tc::tma_load_3d(a_dst + j * (kBlockK * 128), &tmap_w, &full_bar[s], c.cout0 + j * 32,
-                                                kb * kBlockK, P.widx[tap]);
-                        }
-                        tc::tma_load_4d(b_dst, tmap_x, &full_bar[s], kb * kBlockK, gx, gy, c.b0);
+                    const int s = it % kStages;
+                    tc::mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
+                    uint8_t* a_dst = smem + s * stage_bytes;
+                    uint8_t* b_dst = a_dst + kABytes;
+                    tc::mbar_arrive_expect_tx(&full_bar[s], kABytes + P.box_bytes);
+                    if (!p.a_mn) {
+                        tc::tma_load_3d(a_dst, &tmap_w, &full_bar[s], kb * kBlockK, c.cout0, P.widx[tap]);
+                    } else {            // MN-major: four blocks of 32 M-channels x 32 K-rows (4 KB each), one 4-D box
+                        tc::tma_load_4d(a_dst, &tmap_w, &full_bar[s], 0, kb * kBlockK, P.widx[tap], c.cout0 / 32);
                     }
+                    tc::tma_load_4d(b_dst, tmap_x, &full_bar[s], kb * kBlockK, gx, gy, c.b0);
+                    if (++kb == p.kblocks) kb = 0, ++tap;
                 }
             }
         }
@@ -241,9 +246,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         // ===================================================== MMA issuer
         uint32_t it = 0;
         uint32_t tile_n = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_n) {
+        for (int vt = blockIdx.x; vt < p.total_tiles * p.ksplit; vt += gridDim.x, ++tile_n) {
+            const int t = vt / p.ksplit, sp = vt - t * p.ksplit;
             const TileCoord c = decode_tile(p, t);
-            const int n_kblocks = p.phase[c.phase].n_taps * p.kblocks;
+            const int n_k = p.phase[c.phase].n_taps * p.kblocks;
+            const int n_kblocks = n_k * (sp + 1) / p.ksplit - n_k * sp / p.ksplit;       // iterations of this range (>= 1)
             const uint32_t idesc = tc::umma_idesc_tf32(kBlockM, p.phase[c.phase].n_mma, p.a_mn != 0, false);
             const uint32_t acc = tile_n & 1;
             tc::mbar_wait(&tmem_empty[acc], ((tile_n >> 1) & 1) ^ 1);
@@ -288,7 +295,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         uint32_t tile_n = 0;
         const float nw = p.noise ? __ldg(p.noise_w) : 0.f;
         const float alpha = p.alpha, scale = p.scale;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_n) {
+        for (int vt = blockIdx.x; vt < p.total_tiles * p.ksplit; vt += gridDim.x, ++tile_n) {
+            const int t = vt / p.ksplit, sp = vt - t * p.ksplit;
             const TileCoord c = decode_tile(p, t);
             const PhaseDev& P = p.phase[c.phase];
             const uint32_t acc = tile_n & 1;
@@ -324,7 +332,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             tc::mbar_wait(&tmem_full[acc], (tile_n >> 1) & 1);
             tc::tc_fence_after_sync();
             const uint32_t taddr = tmem_base + acc * kMaxN + (static_cast<uint32_t>(quarter * 32) << 16);
-            float* const outp = p.out + co;
+            float* const outp = p.out + co + (long long)sp * p.split_plane;
             const long long out2_delta = DUAL ? (p.out2 - p.out) : 0;
             for (int n0 = 0; n0 < n_valid; n0 += 32) {
                 uint32_t v[32];
@@ -351,6 +359,73 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     }
 }
 
+// Split-K fold: out = epilogue( sum_s ws[s] ), the partial planes added in index order (deterministic).  One thread owns
+// 4 consecutive channels of one output pixel (NHWC).  The TF32 truncation compensation was applied to the partials.
+template <bool ACT>
+__global__ void __launch_bounds__(256)
+conv_fold_kernel(float* __restrict__ out, float* __restrict__ out2, const float* __restrict__ ws, int splits,
+                 long long plane, int cout, int hw, const float* __restrict__ demod, const float* __restrict__ noise,
+                 const float* __restrict__ noise_w, const float* __restrict__ bias, const float* __restrict__ s_next,
+                 float alpha, float scale) {
+    const long long quads = plane / 4;
+    const int cq = cout / 4;
+    const float nw = noise ? __ldg(noise_w) : 0.f;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < quads;
+         q += (long long)gridDim.x * blockDim.x) {
+        const long long pix = q / cq;
+        const int co = (int)(q - pix * cq) * 4;
+        const int b = (int)(pix / hw);
+        float4 a = ld_stream_f4(reinterpret_cast<const float4*>(ws) + q);
+        for (int s = 1; s < splits; ++s) {
+            const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(ws + s * plane) + q);
+            a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
+        }
+        if (demod) {
+            const float4 d = __ldg(reinterpret_cast<const float4*>(demod + (size_t)b * cout + co));
+            a.x *= d.x, a.y *= d.y, a.z *= d.z, a.w *= d.w;
+        }
+        const float nz = noise ? nw * __ldg(noise + pix) : 0.f;
+        if (bias) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + co));
+            a.x += nz + bb.x, a.y += nz + bb.y, a.z += nz + bb.z, a.w += nz + bb.w;
+        } else {
+            a.x += nz, a.y += nz, a.z += nz, a.w += nz;
+        }
+        if (ACT) {
+            a.x = (a.x > 0.f ? a.x : a.x * alpha) * scale, a.y = (a.y > 0.f ? a.y : a.y * alpha) * scale;
+            a.z = (a.z > 0.f ? a.z : a.z * alpha) * scale, a.w = (a.w > 0.f ? a.w : a.w * alpha) * scale;
+        }
+        float4 m = a;
+        if (s_next) {
+            const float4 sn = __ldg(reinterpret_cast<const float4*>(s_next + (size_t)b * cout + co));
+            m.x *= sn.x, m.y *= sn.y, m.z *= sn.z, m.w *= sn.w;
+        }
+        if (out2) {
+            reinterpret_cast<float4*>(out)[q] = a;
+            reinterpret_cast<float4*>(out2)[q] = m;
+        } else {
+            reinterpret_cast<float4*>(out)[q] = m;
+        }
+    }
+}
+
+// Number of K ranges per output tile: 1 unless the launch would leave most SMs idle.
+int choose_ksplit(const rick_conv_geom* g, int total_tiles) {
+    if (total_tiles >= kNumSMs / 2) return 1;
+    long long covered = 0;
+    int min_nk = 1 << 30;
+    for (int i = 0; i < g->n_phases; ++i) {
+        covered += (long long)g->phase[i].rows * g->phase[i].cols;
+        const int nk = g->phase[i].n_taps * (g->cin / kBlockK);
+        if (nk < min_nk) min_nk = nk;
+    }
+    if (covered < (long long)g->out_h * g->out_w) return 1;      // pixels no phase writes would be garbage in the planes
+    int s = kNumSMs / total_tiles;
+    if (s > min_nk / 4) s = min_nk / 4;                           // at least 4 pipeline iterations per range
+    if (s > 32) s = 32;
+    return s < 2 ? 1 : s;
+}
+
 }  // namespace
 }  // namespace rick
 
@@ -359,11 +434,31 @@ extern "C" int rick_conv_tc(void* out, const void* xm, const void* wt, const ric
     if (!g) return RICK_ERR_INVALID_ARGUMENT;
     // packed (n_weight_taps, cout, cin) weights: one K-major matrix per tap
     rick_conv_weight w{wt, (int64_t)g->cin, 1, (int64_t)g->cin * g->cout};
-    return rick_conv_tc_w(out, xm, &w, g, e, stream);
+    return rick_conv_tc_w(out, xm, &w, g, e, nullptr, 0, stream);
+}
+
+namespace rick {
+namespace {
+// tile plan shared by the launcher and the workspace query
+struct TilePlan {
+    int ptw[4], pth[4], nb, tiles_per_group, total_tiles, ksplit;
+};
+int plan_tiles(const rick_conv_geom* g, TilePlan& tp);
+}  // namespace
+}  // namespace rick
+
+extern "C" int64_t rick_conv_tc_workspace(const rick_conv_geom* g) {
+    using namespace rick;
+    if (!g || g->n_phases < 1 || g->n_phases > 4 || g->cout % 32 != 0 || g->cin % kBlockK != 0) return -1;
+    TilePlan tp;
+    if (plan_tiles(g, tp) != RICK_OK) return -1;
+    if (tp.ksplit <= 1) return 0;
+    return (int64_t)tp.ksplit * g->batch * g->out_h * g->out_w * g->cout * 4;
 }
 
 extern "C" int rick_conv_tc_w(void* out, const void* xm, const rick_conv_weight* wd, const rick_conv_geom* g,
-                              const rick_conv_epilogue* e, rick_stream_t stream) {
+                              const rick_conv_epilogue* e, void* workspace, int64_t workspace_bytes,
+                              rick_stream_t stream) {
     using namespace rick;
     if (!out || !xm || !wd || !wd->ptr || !g) return RICK_ERR_INVALID_ARGUMENT;
     const void* wt = wd->ptr;
@@ -382,53 +477,24 @@ extern "C" int rick_conv_tc_w(void* out, const void* xm, const rick_conv_weight*
     EncodeTiledFn encode = get_encode_tiled();
     if (!encode) return RICK_ERR_UNSUPPORTED;
 
-    // ---- pixel tile per phase: tw x th pixels of nb samples, tw*th*nb <= 256, chosen to minimise the padded MMA work
-    //      ceil(cols/tw) * ceil(rows/th) * ceil(batch/nb) * roundup16(tw*th*nb); ties go to the wider tile.
-    //      (33x33 -> 17x11 tiles, 65x65 -> 17x13, 129x129 -> 43x5: the (2H+1)^2 outputs of the transposed conv) ----
-    for (int i = 0; i < g->n_phases; ++i) {
-        if (g->phase[i].n_taps < 1 || g->phase[i].n_taps > 9) return RICK_ERR_INVALID_ARGUMENT;
-        if (g->phase[i].rows < 1 || g->phase[i].cols < 1) return RICK_ERR_INVALID_ARGUMENT;
+    TilePlan tp;
+    {
+        const int rc = plan_tiles(g, tp);
+        if (rc != RICK_OK) return rc;
     }
-    auto choose_tile = [&](int rows, int cols, int& tw, int& th, int& nb) {
-        double best = -1.0;
-        const int max_side = 256 / g->in_stride;               // TMA box extent (in input pixels) must be <= 256
-        for (int kx = 1; kx <= cols; ++kx) {                   // kx tiles across, balanced widths
-            const int w_ = (int)ceil_div(cols, kx);
-            if (w_ > max_side || w_ > kMaxN) continue;
-            int hmax = kMaxN / w_;
-            if (hmax > rows) hmax = rows;
-            if (hmax > max_side) hmax = max_side;
-            if (hmax < 1) continue;
-            const int ky = (int)ceil_div(rows, hmax);
-            const int h_ = (int)ceil_div(rows, ky);            // balanced heights
-            int n_ = 1;
-            if (w_ >= cols && h_ >= rows) {                    // whole image fits: stack samples
-                n_ = kMaxN / (w_ * h_);
-                if (n_ > g->batch) n_ = g->batch;
-                if (n_ < 1) n_ = 1;
-                n_ = (int)ceil_div(g->batch, ceil_div(g->batch, n_));
-            }
-            const int n_mma = ((w_ * h_ * n_ + 15) / 16) * 16;
-            // padded MMA work, with a mild penalty on narrow tiles (weights are re-streamed per tile)
-            const double cost = (double)(ceil_div(cols, w_) * ceil_div(rows, h_) * ceil_div(g->batch, n_)) *
-                                (n_mma + 32.0);
-            if (best < 0 || cost < best - 1e-9) best = cost, tw = w_, th = h_, nb = n_;
-        }
-    };
+    const long long out_elems = (long long)g->batch * g->out_h * g->out_w * g->cout;
+    int ksplit = tp.ksplit;
+    if (ksplit > 1 && (!workspace || workspace_bytes < (int64_t)ksplit * out_elems * 4 || !aligned_to(workspace, 16)))
+        ksplit = 1;                                            // no (or too small a) workspace: plain launch
 
     ConvDev p{};
     p.batch = g->batch, p.cout = g->cout, p.out_h = g->out_h, p.out_w = g->out_w;
     p.in_stride = g->in_stride, p.out_stride = g->out_stride, p.n_phases = g->n_phases;
     p.cout_tiles = (int)ceil_div(g->cout, kBlockM), p.kblocks = g->cin / kBlockK;
     p.a_mn = a_mn ? 1 : 0;
-    int nb_common = 1 << 30;
-    int ptw[4], pth[4];
-    for (int i = 0; i < g->n_phases; ++i) {
-        int tw = 1, th = 1, nb = 1;
-        choose_tile(g->phase[i].rows, g->phase[i].cols, tw, th, nb);
-        ptw[i] = tw, pth[i] = th;
-        if (nb < nb_common) nb_common = nb;
-    }
+    const int nb_common = tp.nb;
+    const int* ptw = tp.ptw;
+    const int* pth = tp.pth;
     int tiles = 0;
     for (int i = 0; i < g->n_phases; ++i) {
         PhaseDev& P = p.phase[i];
@@ -457,11 +523,16 @@ extern "C" int rick_conv_tc_w(void* out, const void* xm, const rick_conv_weight*
     if (total > 0x7fffffffLL) return RICK_ERR_OVERFLOW;
     p.total_tiles = (int)total;
     p.out = static_cast<float*>(out);
+    p.ksplit = ksplit, p.split_plane = out_elems;
     if (e) {
+        if (e->noise && !e->noise_weight) return RICK_ERR_INVALID_ARGUMENT;
+        if (e->out2 && !e->s_next) return RICK_ERR_INVALID_ARGUMENT;
+    }
+    if (ksplit > 1) {
+        p.out = static_cast<float*>(workspace);                // raw partial sums; the epilogue runs in conv_fold_kernel
+    } else if (e) {
         p.out2 = static_cast<float*>(e->out2), p.demod = e->demod, p.noise = e->noise, p.noise_w = e->noise_weight;
         p.bias = e->bias, p.s_next = e->s_next, p.act = e->act, p.alpha = e->alpha, p.scale = e->scale;
-        if (p.noise && !p.noise_w) return RICK_ERR_INVALID_ARGUMENT;
-        if (p.out2 && !p.s_next) return RICK_ERR_INVALID_ARGUMENT;
     }
 
     // ---- tensor maps ----
@@ -478,11 +549,13 @@ extern "C" int rick_conv_tc_w(void* out, const void* xm, const rick_conv_weight*
             rc = encode(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(wt), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        } else {        // MN-major: the GEMM-M channel (cout of THIS call) is contiguous, rows run over GEMM-K (cin)
-            cuuint64_t dims[3] = {(cuuint64_t)g->cout, (cuuint64_t)g->cin, (cuuint64_t)g->n_weight_taps};
-            cuuint64_t strides[2] = {(cuuint64_t)wd->stride_k * 4, tap_stride};
-            cuuint32_t box[3] = {32, kBlockK, 1};
-            rc = encode(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(wt), dims, strides, box, estr,
+        } else {        // MN-major: the GEMM-M channel (cout of THIS call) is contiguous, rows run over GEMM-K (cin).
+            // 4-D view (32 channels, K, taps, M/32): one box delivers the four 32-channel blocks of a tile block-major
+            cuuint64_t dims[4] = {32, (cuuint64_t)g->cin, (cuuint64_t)g->n_weight_taps, (cuuint64_t)(g->cout / 32)};
+            cuuint64_t strides[3] = {(cuuint64_t)wd->stride_k * 4, tap_stride, 128};
+            cuuint32_t box[4] = {32, kBlockK, 1, kBlockM / 32};
+            cuuint32_t estr4[4] = {1, 1, 1, 1};
+            rc = encode(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(wt), dims, strides, box, estr4,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         }
@@ -518,8 +591,84 @@ extern "C" int rick_conv_tc_w(void* out, const void* xm, const rick_conv_weight*
             if (dev >= 0 && dev < 64) attr_done[dev][variant] = true;
         }
     }
-    int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+    const long long visits = (long long)p.total_tiles * ksplit;
+    const int grid = visits < kNumSMs ? (int)visits : kNumSMs;
     kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmap_w, tmap_x[0], tmap_x[1], tmap_x[2], tmap_x[3], p);
     RICK_CHECK_LAUNCH();
+    if (ksplit > 1) {
+        long long blocks = ceil_div(out_elems / 4, 256);
+        if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+        const float* ws = static_cast<const float*>(workspace);
+        const int hw = g->out_h * g->out_w;
+        float* o = static_cast<float*>(out);
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        if (e && e->act)
+            conv_fold_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(o, static_cast<float*>(e->out2), ws, ksplit, out_elems,
+                                                                      g->cout, hw, e->demod, e->noise, e->noise_weight,
+                                                                      e->bias, e->s_next, e->alpha, e->scale);
+        else
+            conv_fold_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(o, e ? static_cast<float*>(e->out2) : nullptr, ws, ksplit,
+                                                                       out_elems, g->cout, hw, e ? e->demod : nullptr,
+                                                                       e ? e->noise : nullptr, e ? e->noise_weight : nullptr,
+                                                                       e ? e->bias : nullptr, e ? e->s_next : nullptr, 0.f, 1.f);
+        RICK_CHECK_LAUNCH();
+    }
     return RICK_OK;
 }
+
+namespace rick {
+namespace {
+int plan_tiles(const rick_conv_geom* g, TilePlan& tp) {
+    // ---- pixel tile per phase: tw x th pixels of nb samples, tw*th*nb <= 256, chosen to minimise the padded MMA work
+    //      ceil(cols/tw) * ceil(rows/th) * ceil(batch/nb) * roundup16(tw*th*nb); ties go to the wider tile.
+    //      (33x33 -> 17x11 tiles, 65x65 -> 17x13, 129x129 -> 43x5: the (2H+1)^2 outputs of the transposed conv) ----
+    for (int i = 0; i < g->n_phases; ++i) {
+        if (g->phase[i].n_taps < 1 || g->phase[i].n_taps > 9) return RICK_ERR_INVALID_ARGUMENT;
+        if (g->phase[i].rows < 1 || g->phase[i].cols < 1) return RICK_ERR_INVALID_ARGUMENT;
+    }
+    auto choose_tile = [&](int rows, int cols, int& tw, int& th, int& nb) {
+        double best = -1.0;
+        const int max_side = 256 / g->in_stride;               // TMA box extent (in input pixels) must be <= 256
+        for (int kx = 1; kx <= cols; ++kx) {                   // kx tiles across, balanced widths
+            const int w_ = (int)ceil_div(cols, kx);
+            if (w_ > max_side || w_ > kMaxN) continue;
+            int hmax = kMaxN / w_;
+            if (hmax > rows) hmax = rows;
+            if (hmax > max_side) hmax = max_side;
+            if (hmax < 1) continue;
+            const int ky = (int)ceil_div(rows, hmax);
+            const int h_ = (int)ceil_div(rows, ky);            // balanced heights
+            int n_ = 1;
+            if (w_ >= cols && h_ >= rows) {                    // whole image fits: stack samples
+                n_ = kMaxN / (w_ * h_);
+                if (n_ > g->batch) n_ = g->batch;
+                if (n_ < 1) n_ = 1;
+                n_ = (int)ceil_div(g->batch, ceil_div(g->batch, n_));
+            }
+            const int n_mma = ((w_ * h_ * n_ + 15) / 16) * 16;
+            // padded MMA work, with a mild penalty on narrow tiles (weights are re-streamed per tile)
+            const double cost = (double)(ceil_div(cols, w_) * ceil_div(rows, h_) * ceil_div(g->batch, n_)) *
+                                (n_mma + 32.0);
+            if (best < 0 || cost < best - 1e-9) best = cost, tw = w_, th = h_, nb = n_;
+        }
+    };
+    int nb_common = 1 << 30;
+    for (int i = 0; i < g->n_phases; ++i) {
+        int tw = 1, th = 1, nb = 1;
+        choose_tile(g->phase[i].rows, g->phase[i].cols, tw, th, nb);
+        tp.ptw[i] = tw, tp.pth[i] = th;
+        if (nb < nb_common) nb_common = nb;
+    }
+    tp.nb = nb_common;
+    int tiles = 0;
+    for (int i = 0; i < g->n_phases; ++i)
+        tiles += (int)(ceil_div(g->phase[i].rows, tp.pth[i]) * ceil_div(g->phase[i].cols, tp.ptw[i]));
+    tp.tiles_per_group = tiles;
+    const long long total = (long long)tiles * ceil_div(g->batch, nb_common) * ceil_div(g->cout, kBlockM);
+    if (total > 0x7fffffffLL) return RICK_ERR_OVERFLOW;
+    tp.total_tiles = (int)total;
+    tp.ksplit = choose_ksplit(g, tp.total_tiles);
+    return RICK_OK;
+}
+}  // namespace
+}  // namespace rick

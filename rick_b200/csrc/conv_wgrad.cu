@@ -11,10 +11,16 @@
 // swizzled layout 32-bit MN-major operands have; tc_common.cuh).  Out-of-range pixels are zero-filled by the TMA unit,
 // which implements the convolution padding and ragged edges for free.
 //
-// Work decomposition: item = (tap, 128-channel block of Cout, <=256-channel block of Cin); the pixel axis of an item is
-// split over `splits` CTAs so that items x splits fills the GPU even for the 128-channel layers (9 items).  CTA = 6 warps:
-//   warp 0  TMA producer: per 32-pixel K-tile 4 boxes of G and Ncin/32 boxes of X into a 4-stage mbarrier ring
-//   warp 1  MMA issuer: 4 x tcgen05.mma.kind::tf32 (M = 128, N = Ncin, K = 8) per stage into one TMEM accumulator
+// Work decomposition: item = (group of taps, 128-channel block of Cout, <=256-channel block of Cin).  Layers with
+// Cin <= 128 take three taps per item (accumulator columns = 3 x Cin <= 384): the G tile is loaded once for the three of
+// them, which lifts the flops per staged byte to the level of the forward kernel (a lone 128 x 128 tile moves 32 KB per
+// 1 MFLOP and starves the tensor pipe: 21 % active in the first profile).  The pixel axis of an item is split over
+// `splits` CTAs so that items x splits is one full wave of the GPU.  CTA = 6 warps:
+//   warp 0  TMA producer: per 32-pixel K-tile ONE 5-D box of G (4 channel blocks) and one per tap of X (Cin/32 channel
+//           blocks each) into an mbarrier ring -- the tensor maps view the channel axis as (C/32, 32) so that a single
+//           copy delivers all 32-channel blocks in the block-major order the MN-major descriptors expect
+//   warp 1  MMA issuer: per stage 4 k-steps of tcgen05.mma.kind::tf32 (M = 128, N <= 256, K = 8; two per k-step when the
+//           item has more than 256 columns) into one TMEM accumulator of up to 512 columns
 //   warps 2-5  epilogue: tcgen05.ld, each thread owns one output channel row and writes 128 B runs of the partial result
 // Partials land in a workspace [split][tap][Cout][Cin]; wgrad_fold adds the splits in a fixed order (deterministic) and
 // writes the gradient with the caller's strides, so it arrives in the parameter's own memory layout.
@@ -24,16 +30,20 @@
 namespace rick {
 namespace {
 
-constexpr int kStages = 4;
+constexpr int kMaxStages = 4;
 constexpr int kBlockM = 128;         // output channels (GEMM-M) per item
-constexpr int kMaxN = 256;           // input channels (GEMM-N) per item
+constexpr int kMaxN = 256;           // input channels per Cin block = columns of one MMA
+constexpr int kMaxCols = 384;        // accumulator columns per item (taps_per_item x n_tile)
 constexpr int kTileK = 32;           // pixels per pipeline stage
 constexpr int kBlockBytes = kTileK * 128;     // one staged block: 32 pixels x 32 channels x 4 B
 constexpr int kThreads = 192;
+constexpr int kSmemBudget = 200 * 1024;
 
 struct WgradDev {
     int batch, cout, cin, n_taps;
     int cin_tiles, n_tile;            // Cin is cut into cin_tiles blocks of n_tile channels (n_tile % 32 == 0, <= 256)
+    int taps_per_item, tap_groups;    // an item accumulates taps_per_item taps side by side (columns = taps x n_tile)
+    int stages, stage_bytes;
     int cout_tiles, items, splits;
     int tw, th, nb, tiles_x, tiles_y, tiles_b, k_tiles;      // pixel tile = tw x th pixels of nb samples = 32 rows
     int g_stride, x_stride;
@@ -46,10 +56,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
                   const __grid_constant__ WgradDev p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int stage_bytes = (kBlockM / 32 + kMaxN / 32) * kBlockBytes;     // fixed stride: every block 1024-aligned
+    const int stage_bytes = p.stage_bytes;                                 // multiple of 4 KB: every block 1024-aligned
+    const int kStages = p.stages;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
-    uint64_t* empty_bar = full_bar + kStages;
-    uint64_t* tmem_full = empty_bar + kStages;
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tmem_full = empty_bar + kMaxStages;
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
     const int warp = threadIdx.x >> 5;
@@ -60,12 +71,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
     const int split = blockIdx.x / p.items;
     const int ci_t = item % p.cin_tiles;
     const int co_t = (item / p.cin_tiles) % p.cout_tiles;
-    const int tap = item / (p.cin_tiles * p.cout_tiles);
+    const int tap0 = (item / (p.cin_tiles * p.cout_tiles)) * p.taps_per_item;
+    const int n_item_taps = min(p.taps_per_item, p.n_taps - tap0);
     const int co0 = co_t * kBlockM, ci0 = ci_t * p.n_tile;
     const int k_begin = (int)((long long)p.k_tiles * split / p.splits);
     const int k_end = (int)((long long)p.k_tiles * (split + 1) / p.splits);
     const int n_blocks = p.n_tile / 32;
-    const uint32_t tmem_cols = p.n_tile <= 32 ? 32u : (p.n_tile <= 64 ? 64u : (p.n_tile <= 128 ? 128u : 256u));
+    const int n_cols = n_item_taps * p.n_tile;                 // accumulator columns in use (<= 384)
+    const uint32_t tmem_cols = n_cols <= 32 ? 32u : (n_cols <= 64 ? 64u : (n_cols <= 128 ? 128u : (n_cols <= 256 ? 256u : 512u)));
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&tmap_g);
@@ -89,7 +102,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
     if (warp == 0) {
         // ===================================================== TMA producer
         if (lane == 0) {
-            const uint32_t bytes = (uint32_t)(kBlockM / 32 + n_blocks) * kBlockBytes;
+            const uint32_t bytes = (uint32_t)(kBlockM / 32 + n_item_taps * n_blocks) * kBlockBytes;
             uint32_t it = 0;
             for (int kt = k_begin; kt < k_end; ++kt, ++it) {
                 const int tx = kt % p.tiles_x;
@@ -102,18 +115,20 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
                 uint8_t* a_dst = smem + s * stage_bytes;
                 uint8_t* b_dst = a_dst + (kBlockM / 32) * kBlockBytes;
                 tc::mbar_arrive_expect_tx(&full_bar[s], bytes);
-                const int gxc = n0 * p.g_stride + p.gx[tap], gyc = m0 * p.g_stride + p.gy[tap];
-                const int xxc = n0 * p.x_stride + p.xx[tap], xyc = m0 * p.x_stride + p.xy[tap];
-#pragma unroll
-                for (int j = 0; j < kBlockM / 32; ++j)
-                    tc::tma_load_4d(a_dst + j * kBlockBytes, &tmap_g, &full_bar[s], co0 + j * 32, gxc, gyc, b0);
-                for (int j = 0; j < n_blocks; ++j)
-                    tc::tma_load_4d(b_dst + j * kBlockBytes, &tmap_x, &full_bar[s], ci0 + j * 32, xxc, xyc, b0);
+                // G does not depend on the tap for an ordinary convolution (gy = gx = 0) but does for the transposed one;
+                // an item's taps share one G tile only in the former case (the host groups taps only then)
+                tc::tma_load_5d(a_dst, &tmap_g, &full_bar[s], 0, n0 * p.g_stride + p.gx[tap0], m0 * p.g_stride + p.gy[tap0],
+                                b0, co0 / 32);
+                for (int j = 0; j < n_item_taps; ++j)
+                    tc::tma_load_5d(b_dst + j * n_blocks * kBlockBytes, &tmap_x, &full_bar[s], 0,
+                                    n0 * p.x_stride + p.xx[tap0 + j], m0 * p.x_stride + p.xy[tap0 + j], b0, ci0 / 32);
             }
         }
     } else if (warp == 1) {
         // ===================================================== MMA issuer
-        const uint32_t idesc = tc::umma_idesc_tf32(kBlockM, p.n_tile, true, true);
+        const int n_first = n_cols <= kMaxN ? n_cols : kMaxN;          // columns of the first MMA of a k-step
+        const uint32_t idesc0 = tc::umma_idesc_tf32(kBlockM, n_first, true, true);
+        const uint32_t idesc1 = tc::umma_idesc_tf32(kBlockM, n_cols > kMaxN ? n_cols - kMaxN : 16, true, true);
         uint32_t it = 0;
         for (int kt = k_begin; kt < k_end; ++kt, ++it) {
             const int s = it % kStages;
@@ -126,7 +141,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
                 for (int k = 0; k < kTileK / 8; ++k) {
                     const uint64_t a_desc = tc::umma_desc_mn_sw128_32b(a_addr + k * 1024, kBlockBytes);
                     const uint64_t b_desc = tc::umma_desc_mn_sw128_32b(b_addr + k * 1024, kBlockBytes);
-                    tc::umma_tf32_ss(tmem_base, a_desc, b_desc, idesc, (it | k) != 0);
+                    tc::umma_tf32_ss(tmem_base, a_desc, b_desc, idesc0, (it | k) != 0);
+                    if (n_cols > kMaxN) {                                   // columns 256.. : the blocks that follow
+                        const uint64_t b_desc1 =
+                            tc::umma_desc_mn_sw128_32b(b_addr + (kMaxN / 32) * kBlockBytes + k * 1024, kBlockBytes);
+                        tc::umma_tf32_ss(tmem_base + kMaxN, a_desc, b_desc1, idesc1, (it | k) != 0);
+                    }
                 }
                 tc::umma_commit(&empty_bar[s]);
                 if (kt == k_end - 1) tc::umma_commit(tmem_full);
@@ -137,26 +157,28 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
         // ===================================================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
         const int quarter = warp & 3;
         const int co = co0 + quarter * 32 + lane;
-        float* dst = p.ws + (((size_t)split * p.n_taps + tap) * p.cout + co) * p.cin + ci0;
         const bool have = k_end > k_begin;
         if (have) {
             tc::mbar_wait(tmem_full, 0);
             tc::tc_fence_after_sync();
         }
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-        for (int n0 = 0; n0 < p.n_tile; n0 += 32) {
-            uint32_t v[32];
-            if (have) {
-                tc::tmem_ld_32x32b_x32(taddr + n0, v);
-                tc::tmem_ld_wait();
-            } else {
+        for (int j = 0; j < n_item_taps; ++j) {
+            float* dst = p.ws + (((size_t)split * p.n_taps + tap0 + j) * p.cout + co) * p.cin + ci0;
+            for (int n0 = 0; n0 < p.n_tile; n0 += 32) {
+                uint32_t v[32];
+                if (have) {
+                    tc::tmem_ld_32x32b_x32(taddr + j * p.n_tile + n0, v);
+                    tc::tmem_ld_wait();
+                } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = 0u;
-            }
-            if (co < p.cout && ci0 + n0 < p.cin) {      // partial last blocks: zero rows / columns, never stored
+                    for (int q = 0; q < 32; ++q) v[q] = 0u;
+                }
+                if (co < p.cout && ci0 + n0 < p.cin) {      // partial last blocks: zero rows / columns, never stored
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<uint4*>(dst + n0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    for (int q = 0; q < 32; q += 4)
+                        *reinterpret_cast<uint4*>(dst + n0 + q) = make_uint4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+                }
             }
         }
         tc::tc_fence_before_sync();
@@ -201,6 +223,7 @@ wgrad_fold_kernel(float* __restrict__ out, const float* __restrict__ ws, int spl
 struct Plan {
     int tw, th, nb, tiles_x, tiles_y, tiles_b, k_tiles;
     int n_tile, cin_tiles, cout_tiles, items, splits;
+    int taps_per_item, tap_groups, stages, stage_bytes;
 };
 
 int validate(const rick_wgrad_geom* g) {
@@ -228,9 +251,19 @@ Plan make_plan(const rick_wgrad_geom* g) {
     P.n_tile = (int)(ceil_div(ceil_div(g->cin, P.cin_tiles), 32) * 32);     // balanced, multiple of 32
     P.cin_tiles = (int)ceil_div(g->cin, P.n_tile);
     P.cout_tiles = (int)ceil_div(g->cout, kBlockM);
-    P.items = g->n_taps * P.cout_tiles * P.cin_tiles;
-    // splits: fill the GPU about twice over, but keep at least 8 K tiles (256 pixels) per CTA
-    int splits = (2 * kNumSMs + P.items - 1) / P.items;
+    // taps that share one G tile: only when G does not move with the tap (ordinary convolutions) and Cin is one block
+    bool g_fixed = true;
+    for (int t = 1; t < g->n_taps; ++t) g_fixed = g_fixed && g->gy[t] == g->gy[0] && g->gx[t] == g->gx[0];
+    P.taps_per_item = 1;
+    if (g_fixed && P.cin_tiles == 1 && g->n_taps % 3 == 0 && 3 * P.n_tile <= kMaxCols) P.taps_per_item = 3;
+    P.tap_groups = (int)ceil_div(g->n_taps, P.taps_per_item);
+    P.items = P.tap_groups * P.cout_tiles * P.cin_tiles;
+    P.stage_bytes = (kBlockM / 32 + P.taps_per_item * (P.n_tile / 32)) * kBlockBytes;
+    P.stages = kSmemBudget / P.stage_bytes;
+    if (P.stages > kMaxStages) P.stages = kMaxStages;
+    // splits: ONE full wave of CTAs (a second, partial wave costs a whole extra round: one CTA per SM is resident), but
+    // at least 8 K tiles (256 pixels) per CTA
+    int splits = kNumSMs / P.items;
     const int by_work = P.k_tiles / 8 > 0 ? P.k_tiles / 8 : 1;
     if (splits > by_work) splits = by_work;
     if (splits < 1) splits = 1;
@@ -266,6 +299,7 @@ extern "C" int rick_conv_wgrad_tc(void* dw, int64_t stride_co, int64_t stride_ci
     WgradDev p{};
     p.batch = g->batch, p.cout = g->cout, p.cin = g->cin, p.n_taps = g->n_taps;
     p.cin_tiles = P.cin_tiles, p.n_tile = P.n_tile, p.cout_tiles = P.cout_tiles, p.items = P.items, p.splits = P.splits;
+    p.taps_per_item = P.taps_per_item, p.tap_groups = P.tap_groups, p.stages = P.stages, p.stage_bytes = P.stage_bytes;
     p.tw = P.tw, p.th = P.th, p.nb = P.nb, p.tiles_x = P.tiles_x, p.tiles_y = P.tiles_y, p.tiles_b = P.tiles_b;
     p.k_tiles = P.k_tiles;
     p.g_stride = g->g_stride, p.x_stride = g->x_stride;
@@ -273,27 +307,29 @@ extern "C" int rick_conv_wgrad_tc(void* dw, int64_t stride_co, int64_t stride_ci
     p.ws = static_cast<float*>(workspace);
 
     CUtensorMap tmap_g, tmap_x;
-    auto make_map = [&](CUtensorMap* m, const void* base, int c, int w, int h, int stride) -> bool {
-        cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)g->batch};
-        cuuint64_t strides[3] = {(cuuint64_t)c * 4, (cuuint64_t)c * w * 4, (cuuint64_t)c * w * h * 4};
+    // 5-D view (32 channels, W, H, B, C/32): one box = `blocks` channel blocks x 32 pixels, written block-major
+    auto make_map = [&](CUtensorMap* m, const void* base, int c, int w, int h, int stride, int blocks) -> bool {
+        cuuint64_t dims[5] = {32, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)g->batch, (cuuint64_t)(c / 32)};
+        cuuint64_t strides[4] = {(cuuint64_t)c * 4, (cuuint64_t)c * w * 4, (cuuint64_t)c * w * h * 4, 128};
         // with a traversal stride s the box spans tw*s pixels and delivers tw of them
-        cuuint32_t box[4] = {32, (cuuint32_t)(P.tw * stride), (cuuint32_t)(P.th * stride), (cuuint32_t)P.nb};
-        cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-        return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, estr,
+        cuuint32_t box[5] = {32, (cuuint32_t)(P.tw * stride), (cuuint32_t)(P.th * stride), (cuuint32_t)P.nb,
+                             (cuuint32_t)blocks};
+        cuuint32_t estr[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1, 1};
+        return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(base), dims, strides, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
     };
-    if (!make_map(&tmap_g, gout, g->cout, g->g_w, g->g_h, g->g_stride)) return RICK_ERR_INVALID_ARGUMENT;
-    if (!make_map(&tmap_x, x, g->cin, g->x_w, g->x_h, g->x_stride)) return RICK_ERR_INVALID_ARGUMENT;
+    if (!make_map(&tmap_g, gout, g->cout, g->g_w, g->g_h, g->g_stride, kBlockM / 32)) return RICK_ERR_INVALID_ARGUMENT;
+    if (!make_map(&tmap_x, x, g->cin, g->x_w, g->x_h, g->x_stride, P.n_tile / 32)) return RICK_ERR_INVALID_ARGUMENT;
 
-    const int stage_bytes = (kBlockM / 32 + kMaxN / 32) * kBlockBytes;
-    const size_t smem = 1024 + (size_t)kStages * stage_bytes + 256;
+    const size_t smem = 1024 + (size_t)P.stages * P.stage_bytes + 256;
     {
         static bool attr_done[64] = {};
         int dev = 0;
         RICK_CUDA_TRY(cudaGetDevice(&dev));
         if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-            RICK_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            RICK_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               1024 + kSmemBudget + 256));
             if (dev >= 0 && dev < 64) attr_done[dev] = true;
         }
     }

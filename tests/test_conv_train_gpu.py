@@ -194,3 +194,52 @@ def test_discriminator_convs_avoid_the_library():
     F.softplus(out).mean().backward()
     assert conv.launch_stats["library"] == before["library"], "a D convolution fell back to the library"
     assert conv.launch_stats["tc"] - before["tc"] >= 3 * (3 * 4 + 1) - 1      # fprop / dgrad / wgrad of 13 convs (no dgrad into from-RGB input needed)
+
+
+@pytest.mark.parametrize("b,h,cin,cout,k,stride,pad", [(2, 4, 512, 512, 3, 1, 1), (4, 8, 512, 512, 3, 1, 1),
+                                                       (4, 16, 512, 512, 3, 1, 1), (4, 9, 512, 512, 3, 2, 0),
+                                                       (2, 8, 128, 64, 3, 1, 1), (4, 4, 544, 512, 3, 1, 1)])
+def test_split_k_equals_unsplit_with_fused_epilogue(b, h, cin, cout, k, stride, pad):
+    """Small maps: the K loop is divided over otherwise idle SMs, partial sums folded in a fixed order with the epilogue
+    (demod, noise, bias, leaky-ReLU, pre-modulated second output) applied by the fold kernel.  Must equal the one-kernel
+    path up to fp32 summation order, be deterministic, and actually be in use for these shapes."""
+    import ctypes
+    from rick_b200 import _lib
+    from rick_b200 import conv_tc as ct
+    x = _rand(b, h, h, cin, seed=1)
+    wgt = _cl(_rand(cout, cin, k, k, seed=2) / math.sqrt(cin * k * k))
+    geom = ct.geom_conv(b, h, h, cin, cout, k, stride, pad)
+    assert _lib.lib().rick_conv_tc_workspace(ctypes.byref(geom)) > 0, "expected a split-K plan for this shape"
+    oh = geom.out_h
+    kw = dict(demod=_rand(b, cout, seed=3).abs() + 0.5, noise=_rand(b, oh, oh, seed=4), noise_weight=_rand(1, seed=5),
+              bias=_rand(cout, seed=6), act=True, s_next=_rand(b, cout, seed=7), want_out2=True)
+    ct.SPLIT_K = False
+    try:
+        want, want2 = ct.conv_tc_nhwc(x, wgt, geom, **kw)
+        plain_want = ct.conv_tc_nhwc(x, wgt, geom)
+    finally:
+        ct.SPLIT_K = True
+    got, got2 = ct.conv_tc_nhwc(x, wgt, geom, **kw)
+    # fp32 summation order differs (K ranges are added after the fact): a few ulps of the output scale
+    assert _err(got, want) < 5e-5 and _err(got2, want2) < 5e-5
+    assert _err(ct.conv_tc_nhwc(x, wgt, geom), plain_want) < 5e-5
+    again, again2 = ct.conv_tc_nhwc(x, wgt, geom, **kw)
+    assert torch.equal(again, got) and torch.equal(again2, got2)
+
+
+def test_split_k_polyphase_and_transposed_weight():
+    """split-K through the 4-phase transposed convolution and through an MN-major (data-gradient) weight operand"""
+    from rick_b200 import conv_tc as ct
+    b, h, cin, cout = 2, 8, 512, 512
+    x = _rand(b, h, h, cin, seed=11)
+    wgt = _cl(_rand(cout, cin, 3, 3, seed=12) / math.sqrt(cin * 9))
+    for geom, tr, xin in ((ct.geom_conv_transpose_s2(b, h, h, cin, cout), False, x),
+                          (ct.geom_conv_dgrad(b, h, h, cin, cout, 3, 1, 1), True, _rand(b, h, h, cout, seed=13)),
+                          (ct.geom_conv_dgrad(b, 2 * h + 1, 2 * h + 1, cin, cout, 3, 2, 0), True, _rand(b, h, h, cout, seed=14))):
+        ct.SPLIT_K = False
+        try:
+            want = ct.conv_tc_nhwc(xin, wgt, geom, transpose_weight=tr)
+        finally:
+            ct.SPLIT_K = True
+        got = ct.conv_tc_nhwc(xin, wgt, geom, transpose_weight=tr)
+        assert _err(got, want) < 5e-5
