@@ -305,6 +305,28 @@ RICK_API int rick_styled_epilogue_bwd_nhwc(void* ga, float* gdemod, float* gbias
                                            float scale, rick_stream_t stream);
 
 
+/* ------------------------------------------------------------------------------------------- glue kernels
+ * wsq[co][ci] = sum_tap w[co*stride_co + ci*stride_ci + tap*stride_tap]^2: the (Cout, Cin) table the demodulation of
+ * ModulatedConv2d is computed from (model_probe_tune.py:249-251; ``w.pow(2).sum([2, 3])`` in one pass, no temporary). */
+RICK_API int rick_weight_sqsum(float* out, const float* w, int cout, int cin, int taps, int64_t stride_co,
+                               int64_t stride_ci, int64_t stride_tap, rick_stream_t stream);
+
+/* `count` small-batch EqualLinear layers in one launch (model_probe_tune.py:139-173: the 8 mapping-network layers, the
+ * style -> channel modulation layer of every ModulatedConv2d):
+ *     y[l][b, r] = act( w_scale[l] * sum_k w[l][r, k] * x[l][b, k] + b_scale[l] * bias[l][r] ),   b < batch <= 8
+ * w[l] (out_dim[l], in_dim) row-major, x[l] rows x_stride[l] elements apart, y[l] (batch, out_dim[l]) contiguous,
+ * bias[l] may be NULL.  act != 0: leaky-ReLU(alpha) * act_scale (fused_leaky_relu).  pixelnorm != 0: x is divided by
+ * sqrt(mean_k x^2 + 1e-8) first (PixelNorm, :21-26).  Tables are HOST arrays.  in_dim % 4 == 0.
+ * rick_linear_multi_wgrad: gw[l][r, k] = w_scale[l] * sum_b gy[l][b, r] * x[l][b, k] and
+ * gbias[l][r] = b_scale[l] * sum_b gy[l][b, r] (either may be NULL per layer). */
+RICK_API int rick_linear_multi(float* const* y, const float* const* w, const float* const* bias, const float* const* x,
+                               const int64_t* x_stride, const int* out_dim, const float* w_scale, const float* b_scale,
+                               int count, int batch, int in_dim, int act, float alpha, float act_scale, int pixelnorm,
+                               rick_stream_t stream);
+RICK_API int rick_linear_multi_wgrad(float* const* gw, float* const* gbias, const float* const* gy, const float* const* x,
+                                     const int64_t* x_stride, const int* out_dim, const float* w_scale,
+                                     const float* b_scale, int count, int batch, int in_dim, rick_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

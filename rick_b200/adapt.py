@@ -9,7 +9,9 @@ idle waiting for the host:
   * No ``.item()`` / ``empty_cache()`` inside the iteration (the reference has ten such syncs, e.g. train:425, 596-603).
   * The D step runs G under ``no_grad`` and the G step differentiates only w.r.t. G's parameters.  Both are
     result-preserving: the reference back-propagates into the other network and then discards those gradients with
-    ``zero_grad()`` (train:401-420, 516).
+    ``zero_grad()`` (train:401-420, 516).  Likewise the mapping network (``style.*``) is evaluated without autograd:
+    it is not among the parameters handed to the optimiser (train:908-917 keeps names containing 'convs'), and the
+    path-length penalty differentiates w.r.t. its OUTPUT (train:548-566).
   * Optimiser selection, betas, warm-up gating, regulariser schedule, EMA and the order in which random numbers are
     consumed are the reference's.
 
@@ -231,6 +233,15 @@ class RickAdapter:
         self.masks_d.update(self.acc_d.as_dict(), cfg.fisher_quantile, cfg.prune_quantile)
 
     # ------------------------------------------------------------------------------------------ one iteration
+    @torch.no_grad()
+    def _latents(self, z: List[torch.Tensor], inject: Optional[int]) -> torch.Tensor:
+        """(B, n_latent, D) latent of ``Generator.forward(z, inject_index=inject)`` (model_probe_tune.py:532-560)."""
+        n = self.g.n_latent
+        w = [self.g.map_latent(zz) for zz in z]
+        if len(w) < 2:
+            return w[0].unsqueeze(1).repeat(1, n, 1)
+        return torch.cat([w[0].unsqueeze(1).repeat(1, inject, 1), w[1].unsqueeze(1).repeat(1, n - inject, 1)], 1)
+
     def _gate_warmup(self, i: int):
         warm = i < self.cfg.warmup_iter
         for n, p in self.d_named.items():
@@ -249,11 +260,9 @@ class RickAdapter:
         z = draws.mixing_latents(cfg.batch, cfg.latent, cfg.mixing)
         inject = draws.randint(1, self.g.n_latent - 1) if len(z) == 2 else None
         with torch.no_grad():
-            if self.fg is not None:
-                self.fg.refresh()                       # G's weights moved since the last call
-                fake_img, _ = self.fg(z, inject_index=inject, noise=noise_of(cfg.batch))
-            else:
-                fake_img, _ = self.g(z, inject_index=inject, noise=noise_of(cfg.batch))
+            lat = self._latents(z, inject)
+            gen = self.fg if self.fg is not None else self.g     # fg reads G's parameters in place: always current
+            fake_img, _ = gen([lat], input_is_latent=True, noise=noise_of(cfg.batch))
         fake_pred, real_pred = d_pair(self.d, fake_img, real_img)
         d_loss = d_logistic_loss(real_pred, fake_pred)
         out["d"], out["real_score"], out["fake_score"] = d_loss.detach(), real_pred.mean().detach(), fake_pred.mean().detach()
@@ -285,7 +294,7 @@ class RickAdapter:
         z = draws.mixing_latents(cfg.batch, cfg.latent, cfg.mixing)
         inject = draws.randint(1, self.g.n_latent - 1) if len(z) == 2 else None
         if after_warmup:
-            fake_img, _ = self.g(z, inject_index=inject, noise=noise_of(cfg.batch))
+            fake_img, _ = self.g([self._latents(z, inject)], input_is_latent=True, noise=noise_of(cfg.batch))
             fake_pred, _ = self.d(fake_img)
             g_loss = g_nonsaturating_loss(fake_pred)
             self.g.zero_grad(set_to_none=True)
@@ -294,7 +303,7 @@ class RickAdapter:
             self._optim_step("g", True, ema=not path_iter)
         else:
             with torch.no_grad():                       # warm-up: the loss is only logged (train:518-519)
-                fake_img, _ = self.g(z, inject_index=inject, noise=noise_of(cfg.batch))
+                fake_img, _ = self.g([self._latents(z, inject)], input_is_latent=True, noise=noise_of(cfg.batch))
                 g_loss = g_nonsaturating_loss(self.d(fake_img)[0])
         out["g"] = g_loss.detach()
 
@@ -303,7 +312,8 @@ class RickAdapter:
             pb = max(1, cfg.batch // cfg.path_batch_shrink)
             z = draws.mixing_latents(pb, cfg.latent, cfg.mixing)
             inject = draws.randint(1, self.g.n_latent - 1) if len(z) == 2 else None
-            fake_img, latents = self.g(z, return_latents=True, inject_index=inject, noise=noise_of(pb))
+            lat = self._latents(z, inject).requires_grad_(True)
+            fake_img, latents = self.g([lat], input_is_latent=True, return_latents=True, noise=noise_of(pb))
             path_loss, self.mean_path_length, path_lengths = g_path_regularize(
                 fake_img, latents, self.mean_path_length, draws.normal(*fake_img.shape))
             self.g.zero_grad(set_to_none=True)

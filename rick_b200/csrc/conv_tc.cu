@@ -376,7 +376,16 @@ conv_fold_kernel(float* __restrict__ out, float* __restrict__ out2, const float*
         const int co = (int)(q - pix * cq) * 4;
         const int b = (int)(pix / hw);
         float4 a = ld_stream_f4(reinterpret_cast<const float4*>(ws) + q);
-        for (int s = 1; s < splits; ++s) {
+        int s = 1;
+        for (; s + 4 <= splits; s += 4) {        // four loads in flight (a 32-way split is otherwise 32 serial L2 trips)
+            const float4 v0 = ld_stream_f4(reinterpret_cast<const float4*>(ws + (s + 0) * plane) + q);
+            const float4 v1 = ld_stream_f4(reinterpret_cast<const float4*>(ws + (s + 1) * plane) + q);
+            const float4 v2 = ld_stream_f4(reinterpret_cast<const float4*>(ws + (s + 2) * plane) + q);
+            const float4 v3 = ld_stream_f4(reinterpret_cast<const float4*>(ws + (s + 3) * plane) + q);
+            a.x = (((a.x + v0.x) + v1.x) + v2.x) + v3.x, a.y = (((a.y + v0.y) + v1.y) + v2.y) + v3.y;
+            a.z = (((a.z + v0.z) + v1.z) + v2.z) + v3.z, a.w = (((a.w + v0.w) + v1.w) + v2.w) + v3.w;
+        }
+        for (; s < splits; ++s) {
             const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(ws + s * plane) + q);
             a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
         }

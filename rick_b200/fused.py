@@ -14,7 +14,9 @@ each StyledConv is one or two kernels:
     skip upsample         rick_upfirdn2d      on the 3-channel NCHW image
 
 Per-layer styles / demodulation coefficients are (B, C) matrices computed up front (tiny cuBLAS calls).
-Weights are repacked to (taps, Cout, Cin) once and cached until ``refresh()``.
+The convolution weights are read IN PLACE: ModulatedConv2d stores them [Cout][k][k][Cin], which the kernel consumes
+through a strided tensor map, so the executor holds views of the parameters and is always current -- no re-packing
+after an optimiser step (``refresh()`` is kept as a no-op for callers written against the packing version).
 """
 from __future__ import annotations
 
@@ -25,14 +27,14 @@ from torch.nn import functional as F
 
 from . import conv_tc as ct
 from .op import upfirdn2d
+from .op.glue import weight_sqsum
 
 
 class _ConvPlan:
     def __init__(self, sconv):
         mc = sconv.conv
-        w = (mc.weight[0] * mc.scale).detach()
-        self.wt = ct.pack_weight(w)                              # (9, Cout, Cin)
-        self.wsq = w.pow(2).sum([2, 3]).contiguous()             # (Cout, Cin) for the demodulation
+        self.w = mc.weight.detach().squeeze(0)                   # (Cout, Cin, 3, 3) VIEW of the parameter's memory
+        self.wscale = mc.scale                                   # equalised-lr scale: rides on the style (see below)
         self.cin, self.cout = mc.in_channel, mc.out_channel
         self.upsample = mc.upsample
         self.blur_taps = mc.blur.kernel.detach().contiguous() if mc.upsample else None
@@ -46,7 +48,8 @@ class _ConvPlan:
 class _RgbPlan:
     def __init__(self, rgb):
         mc = rgb.conv
-        self.w = (mc.weight[0, :, :, 0, 0] * mc.scale).detach().contiguous()      # (3, Cin)
+        self.w = mc.weight.detach()[0, :, :, 0, 0]                                  # (3, Cin) view
+        self.wscale = mc.scale
         self.mod = mc.modulation
         self.bias = rgb.bias.detach().reshape(3).contiguous()
         self.up = rgb.upsample if hasattr(rgb, "upsample") else None
@@ -68,13 +71,20 @@ class FusedGenerator:
         return all(ct.supported(c.conv.in_channel, c.conv.out_channel) for c in convs)
 
     def refresh(self):
-        """Re-pack weights after the parameters changed (optimiser step / EMA update)."""
+        """(Re)build the per-layer plans.  The plans hold VIEWS of the parameters, so this is only needed when a
+        parameter tensor was replaced (not when its values changed)."""
         g = self.g
         self.convs: List[_ConvPlan] = [_ConvPlan(g.conv1)] + [_ConvPlan(c) for c in g.convs]
         self.rgbs: List[_RgbPlan] = [_RgbPlan(g.to_rgb1)] + [_RgbPlan(r) for r in g.to_rgbs]
         for p in self.convs:
             if not ct.supported(p.cin, p.cout):
                 raise RuntimeError(f"FusedGenerator: layer {p.cin}->{p.cout} is outside the tcgen05 kernel's shapes")
+
+    @staticmethod
+    def _weight(p):
+        """the layer's weight as the kernel wants it: in place when stored channels-last, else packed per call"""
+        w = p.w
+        return w if w.is_contiguous(memory_format=torch.channels_last) else ct.pack_weight(w)
 
     @torch.no_grad()
     def __call__(self, styles, return_latents=False, inject_index=None, truncation=1, truncation_latent=None,
@@ -90,9 +100,19 @@ class FusedGenerator:
         # latent index per StyledConv / ToRGB (model_probe_tune.py:567-582)
         conv_idx = [0] + [i for blk in range(len(g.to_rgbs)) for i in (1 + 2 * blk, 2 + 2 * blk)]
         rgb_idx = [1] + [3 + 2 * blk for blk in range(len(g.to_rgbs))]
-        s = [p.mod(latent[:, i]).contiguous() for p, i in zip(self.convs, conv_idx)]                  # (B, Cin)
-        demod = [torch.rsqrt(F.linear(si.pow(2), p.wsq) + 1e-8).contiguous() for p, si in zip(self.convs, s)]
-        s_rgb = [p.mod(latent[:, i]) for p, i in zip(self.rgbs, rgb_idx)]
+        # every layer's modulation from one launch (order of Generator._modulated(): conv1, rgb1, then up / conv / rgb)
+        latent = latent.contiguous()
+        mods = g.all_modulations(latent)
+        if mods is not None:
+            raw_conv = [mods[0]] + [mods[2 + 3 * blk + j] for blk in range(len(g.to_rgbs)) for j in (0, 1)]
+            raw_rgb = [mods[1]] + [mods[4 + 3 * blk] for blk in range(len(g.to_rgbs))]
+        else:
+            raw_conv = [p.mod(latent[:, i]) for p, i in zip(self.convs, conv_idx)]
+            raw_rgb = [p.mod(latent[:, i]) for p, i in zip(self.rgbs, rgb_idx)]
+        # conv(x * s, scale * W) == conv(x * (scale * s), W): the equalised-lr scale rides on the (B, Cin) style
+        s = [(r * p.wscale).contiguous() for p, r in zip(self.convs, raw_conv)]                       # (B, Cin)
+        demod = [torch.rsqrt(F.linear(si.pow(2), weight_sqsum(p.w)) + 1e-8).contiguous() for p, si in zip(self.convs, s)]
+        s_rgb = [r * p.wscale for p, r in zip(self.rgbs, raw_rgb)]
 
         def layer_noise(li, h, w):
             n = noise[li]
@@ -111,7 +131,7 @@ class FusedGenerator:
         xm = (x0 * s[0][:, None, None, :]).contiguous()
         p0 = self.convs[0]
         has_next = len(self.convs) > 1
-        res = ct.conv_tc_nhwc(xm, p0.wt, ct.geom_conv(b, 4, 4, p0.cin, p0.cout, 3, 1, 1), demod=demod[0],
+        res = ct.conv_tc_nhwc(xm, self._weight(p0), ct.geom_conv(b, 4, 4, p0.cin, p0.cout, 3, 1, 1), demod=demod[0],
                               noise=layer_noise(0, 4, 4), noise_weight=p0.noise_w, bias=p0.bias, act=True,
                               alpha=p0.alpha, scale=p0.scale, s_next=s[1] if has_next else None, want_out2=has_next)
         y, ym = res if has_next else (res, None)
@@ -122,13 +142,13 @@ class FusedGenerator:
             li = 1 + 2 * blk
             # upsampling StyledConv: transposed conv (raw accumulators) -> blur with the fused epilogue; only the copy
             # pre-modulated for the following conv is written
-            raw = ct.conv_tc_nhwc(ym, up.wt, ct.geom_conv_transpose_s2(b, h, h, up.cin, up.cout))
+            raw = ct.conv_tc_nhwc(ym, self._weight(up), ct.geom_conv_transpose_s2(b, h, h, up.cin, up.cout))
             h *= 2
             ym = ct.blur_nhwc(raw, up.blur_taps, up.blur_pad, demod=demod[li], noise=layer_noise(li, h, h),
                               noise_weight=up.noise_w, bias=up.bias, act=True, alpha=up.alpha, scale=up.scale,
                               s_next=s[li + 1])
             last = blk == len(g.to_rgbs) - 1
-            res = ct.conv_tc_nhwc(ym, cv.wt, ct.geom_conv(b, h, h, cv.cin, cv.cout, 3, 1, 1), demod=demod[li + 1],
+            res = ct.conv_tc_nhwc(ym, self._weight(cv), ct.geom_conv(b, h, h, cv.cin, cv.cout, 3, 1, 1), demod=demod[li + 1],
                                   noise=layer_noise(li + 1, h, h), noise_weight=cv.noise_w, bias=cv.bias, act=True,
                                   alpha=cv.alpha, scale=cv.scale, s_next=None if last else s[li + 2],
                                   want_out2=not last)
@@ -140,7 +160,7 @@ class FusedGenerator:
         import random
         g = self.g
         if not input_is_latent:
-            styles = [g.style(s) for s in styles]
+            styles = [g.map_latent(s) for s in styles]
         if truncation < 1:
             styles = [truncation_latent + truncation * (s - truncation_latent) for s in styles]
         if len(styles) < 2:

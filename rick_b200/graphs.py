@@ -87,8 +87,11 @@ class GraphedRickAdapter(RickAdapter):
     def _latent(self, batch: int, key: str) -> torch.Tensor:
         cfg = self.cfg
         z = self._z[key] if self.explicit_inputs else torch.randn(2, batch, cfg.latent, device=self.device)
-        w1, w2 = self.g.style(z[0]), self.g.style(z[1])
-        return torch.where(self._layer < self._inject[key], w1.unsqueeze(1), w2.unsqueeze(1))
+        # the mapping network is not among the trained parameters (train:908-917): no autograd through it, which is
+        # result-preserving and lets both latents go through the fused forward in one pass
+        with torch.no_grad():
+            w = self.g.map_latent(z.reshape(2 * batch, cfg.latent)).reshape(2, batch, cfg.latent)
+            return torch.where(self._layer < self._inject[key], w[0].unsqueeze(1), w[1].unsqueeze(1))
 
     def _layer_noise(self, key: str):
         return self._noise[key] if self.explicit_inputs else None
@@ -98,7 +101,6 @@ class GraphedRickAdapter(RickAdapter):
         with torch.no_grad():
             latent = self._latent(cfg.batch, "d")
             if self.fg is not None:
-                self.fg.refresh()
                 fake_img, _ = self.fg([latent], input_is_latent=True, noise=self._layer_noise("d"))
             else:
                 fake_img, _ = self.g([latent], input_is_latent=True, noise=self._layer_noise("d"))
@@ -137,7 +139,7 @@ class GraphedRickAdapter(RickAdapter):
     def _body_path(self):
         cfg = self.cfg
         pb = max(1, cfg.batch // cfg.path_batch_shrink)
-        latent = self._latent(pb, "path")
+        latent = self._latent(pb, "path").requires_grad_(True)
         fake_img, latents = self.g([latent], input_is_latent=True, return_latents=True, noise=self._layer_noise("path"))
         path_noise = self._path_noise if self.explicit_inputs else torch.randn_like(fake_img)
         path_loss, path_mean, path_lengths = g_path_regularize(fake_img, latents, self.mean_path_length, path_noise)

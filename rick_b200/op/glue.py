@@ -1,0 +1,167 @@
+"""Fused stand-ins for short chains of ATen launches around the convolutions (rick_b200/csrc/glue_ops.cu).
+
+    weight_sqsum(w)     (Cout, Cin, k, k) -> (Cout, Cin): sum over the taps of w**2, the table ModulatedConv2d's
+                        demodulation is computed from (model_probe_tune.py:249-251), in one pass for any weight layout
+
+Every op is differentiable to any order: the backward formulas are written with differentiable torch ops.
+"""
+from __future__ import annotations
+
+import torch
+from torch.autograd import Function
+
+from .. import _lib
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _even_taps(w: torch.Tensor) -> bool:
+    kh, kw = w.shape[2], w.shape[3]
+    return kh * kw == 1 or (w.stride(2) == kw * w.stride(3))
+
+
+class _WeightSqSum(Function):
+    @staticmethod
+    def forward(ctx, w):
+        co, ci, kh, kw = w.shape
+        out = torch.empty(co, ci, dtype=torch.float32, device=w.device)
+        with torch.cuda.device(w.device):
+            _lib.check(_lib.lib().rick_weight_sqsum(out.data_ptr(), w.data_ptr(), co, ci, kh * kw, w.stride(0), w.stride(1),
+                                                    w.stride(3) if kh * kw > 1 else 1, _stream()), "rick_weight_sqsum")
+        ctx.save_for_backward(w)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (w,) = ctx.saved_tensors
+        return (2.0 * g)[:, :, None, None] * w           # keeps w's memory layout; differentiable again
+
+
+def weight_sqsum(w: torch.Tensor) -> torch.Tensor:
+    """``w.pow(2).sum([2, 3])`` for a (Cout, Cin, k, k) weight."""
+    if w.is_cuda and w.dtype == torch.float32 and w.dim() == 4 and _even_taps(w):
+        return _WeightSqSum.apply(w)
+    return w.pow(2).sum([2, 3])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# many small-batch EqualLinear layers in one launch
+# ---------------------------------------------------------------------------------------------------------------
+import ctypes
+from typing import List, Optional, Sequence
+
+
+def _f32_table(vals):
+    return (ctypes.c_float * len(vals))(*[float(v) for v in vals])
+
+
+def _i32_table(vals):
+    return (ctypes.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def _linear_multi_launch(latent, idx, weights, biases, w_scales, b_scales, act, alpha, act_scale, pixelnorm):
+    b, n_lat, d = latent.shape
+    outs = [torch.empty(b, w.shape[0], dtype=torch.float32, device=latent.device) for w in weights]
+    base, row = latent.data_ptr(), n_lat * d
+    with torch.cuda.device(latent.device):
+        rc = _lib.lib().rick_linear_multi(
+            _lib.ptr_table([o.data_ptr() for o in outs]), _lib.ptr_table([w.data_ptr() for w in weights]),
+            _lib.ptr_table([None if bb is None else bb.data_ptr() for bb in biases]),
+            _lib.ptr_table([base + 4 * d * i for i in idx]), _lib.i64_table([row] * len(idx)),
+            _i32_table([w.shape[0] for w in weights]), _f32_table(w_scales), _f32_table(b_scales), len(weights), b, d,
+            int(act), float(alpha), float(act_scale), int(pixelnorm), _stream())
+    _lib.check(rc, "rick_linear_multi")
+    return outs
+
+
+class _LinearMulti(Function):
+    """y_l = w_scale_l * latent[:, idx_l] @ W_l^T + b_scale_l * bias_l for a list of layers, one launch forward and one
+    for all weight / bias gradients."""
+
+    @staticmethod
+    def forward(ctx, latent, idx, w_scales, b_scales, *wb):
+        weights, biases = list(wb[0::2]), list(wb[1::2])
+        ctx.idx, ctx.w_scales, ctx.b_scales = tuple(idx), tuple(w_scales), tuple(b_scales)
+        ctx.n = len(weights)
+        ctx.has_bias = [bb is not None for bb in biases]
+        ctx.save_for_backward(latent, *weights)
+        return tuple(_linear_multi_launch(latent, idx, weights, biases, w_scales, b_scales, False, 0.2, 1.0, False))
+
+    @staticmethod
+    def backward(ctx, *gys):
+        latent, *weights = ctx.saved_tensors
+        n, idx, ws, bs = ctx.n, ctx.idx, ctx.w_scales, ctx.b_scales
+        need_lat = ctx.needs_input_grad[0]
+        grads: List[Optional[torch.Tensor]] = [None] * (2 * n)
+        g_lat = None
+        if torch.is_grad_enabled():                      # create_graph (path-length): differentiable formulas
+            per_idx = {}
+            for l in range(n):
+                gy = gys[l]
+                if gy is None:
+                    continue
+                x = latent[:, idx[l]]
+                if ctx.needs_input_grad[4 + 2 * l]:
+                    grads[2 * l] = ws[l] * (gy.t() @ x)
+                if ctx.has_bias[l] and ctx.needs_input_grad[5 + 2 * l]:
+                    grads[2 * l + 1] = bs[l] * gy.sum(0)
+                if need_lat:
+                    t = ws[l] * (gy @ weights[l])
+                    per_idx[idx[l]] = t if idx[l] not in per_idx else per_idx[idx[l]] + t
+            if need_lat:
+                zero = latent.new_zeros(latent.shape[0], latent.shape[2])
+                g_lat = torch.stack([per_idx.get(i, zero) for i in range(latent.shape[1])], 1)
+            return (g_lat, None, None, None) + tuple(grads)
+        live = [l for l in range(n) if gys[l] is not None]
+        if live:
+            gw = {l: (torch.empty_like(weights[l]) if ctx.needs_input_grad[4 + 2 * l] else None) for l in live}
+            gb = {l: (torch.empty(weights[l].shape[0], dtype=torch.float32, device=latent.device)
+                      if ctx.has_bias[l] and ctx.needs_input_grad[5 + 2 * l] else None) for l in live}
+            gyc = {l: gys[l].contiguous() for l in live}
+            b, n_lat, d = latent.shape
+            base, row = latent.data_ptr(), n_lat * d
+            with torch.cuda.device(latent.device):
+                rc = _lib.lib().rick_linear_multi_wgrad(
+                    _lib.ptr_table([None if gw[l] is None else gw[l].data_ptr() for l in live]),
+                    _lib.ptr_table([None if gb[l] is None else gb[l].data_ptr() for l in live]),
+                    _lib.ptr_table([gyc[l].data_ptr() for l in live]), _lib.ptr_table([base + 4 * d * idx[l] for l in live]),
+                    _lib.i64_table([row] * len(live)), _i32_table([weights[l].shape[0] for l in live]),
+                    _f32_table([ws[l] for l in live]), _f32_table([bs[l] for l in live]), len(live), b, d, _stream())
+            _lib.check(rc, "rick_linear_multi_wgrad")
+            for l in live:
+                grads[2 * l], grads[2 * l + 1] = gw[l], gb[l]
+            if need_lat:                                  # only the path-length / Fisher passes differentiate the latents
+                g_lat = torch.zeros_like(latent)
+                for l in live:
+                    g_lat[:, idx[l]].addmm_(gyc[l], weights[l], alpha=ws[l])
+        return (g_lat, None, None, None) + tuple(grads)
+
+
+def linear_multi(latent: torch.Tensor, idx: Sequence[int], weights: Sequence[torch.Tensor],
+                 biases: Sequence[Optional[torch.Tensor]], w_scales: Sequence[float], b_scales: Sequence[float]):
+    """[w_scales[l] * latent[:, idx[l]] @ weights[l].T + b_scales[l] * biases[l] for l ...] -- the modulation layers of
+    all ModulatedConv2d modules of a generator in one launch.  ``latent`` is (B, n_latent, D) contiguous fp32."""
+    wb = []
+    for w, bb in zip(weights, biases):
+        wb += [w, bb]
+    return list(_LinearMulti.apply(latent, tuple(idx), tuple(w_scales), tuple(b_scales), *wb))
+
+
+def linear_multi_ok(latent: torch.Tensor, weights: Sequence[torch.Tensor]) -> bool:
+    return (latent.is_cuda and latent.dtype == torch.float32 and latent.dim() == 3 and latent.is_contiguous()
+            and latent.shape[0] <= 8 and latent.shape[2] % 4 == 0
+            and all(w.is_contiguous() and w.dtype == torch.float32 and w.shape[1] == latent.shape[2] for w in weights))
+
+
+@torch.no_grad()
+def mapping_network(z: torch.Tensor, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor], w_scale: float,
+                    b_scale: float, negative_slope: float = 0.2, act_scale: float = 2 ** 0.5) -> torch.Tensor:
+    """PixelNorm + the chain of EqualLinear(activation='fused_lrelu') layers (model_probe_tune.py:383-392), forward only:
+    one launch per layer (the normalisation rides on the first)."""
+    x = z.contiguous().unsqueeze(1)                       # (B, 1, D)
+    for i, (w, bb) in enumerate(zip(weights, biases)):
+        (y,) = _linear_multi_launch(x, [0], [w], [bb], [w_scale], [b_scale], True, negative_slope, act_scale, i == 0)
+        x = y.unsqueeze(1)
+    return x.squeeze(1)

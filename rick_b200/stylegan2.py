@@ -28,6 +28,8 @@ from torch.nn import functional as F
 
 from . import conv as _conv
 from .op import FusedLeakyReLU, fused_leaky_relu, upfirdn2d
+from .op import glue as _glue
+from .op.glue import weight_sqsum
 from .op.scale import scale_all
 
 
@@ -39,6 +41,7 @@ _CHANNELS_LAST = os.environ.get("RICK_CHANNELS_LAST", "1") != "0"
 
 _PRESCALE = os.environ.get("RICK_PRESCALE", "1") != "0"           # one multi-tensor launch for all equalised-lr multipliers
 _FUSED_STYLED = os.environ.get("RICK_FUSED_STYLED", "1") != "0"   # fused modulate / demod-noise-bias-act ops in StyledConv
+_FUSED_LINEARS = os.environ.get("RICK_FUSED_LINEARS", "1") != "0"  # mapping network / all modulation layers: one launch each
 
 
 def set_fused_styled(flag: bool) -> None:
@@ -250,16 +253,18 @@ class ModulatedConv2d(nn.Module):
         return (f"{self.__class__.__name__}({self.in_channel}, {self.out_channel}, {self.kernel_size}, "
                 f"upsample={self.upsample}, downsample={self.downsample})")
 
-    def forward(self, input, style, epilogue=None):
+    def forward(self, input, style, epilogue=None, s=None):
         """``epilogue`` = (noise, noise_weight, bias, slope, scale): StyledConv hands its NoiseInjection + FusedLeakyReLU
-        down so that demodulation, noise, bias and activation run as one fused op behind the convolution."""
-        s = self.modulation(style)                                   # (B, Cin)
+        down so that demodulation, noise, bias and activation run as one fused op behind the convolution.
+        ``s``: this layer's modulation ``self.modulation(style)`` when the generator computed all of them in one launch."""
+        if s is None:
+            s = self.modulation(style)                               # (B, Cin)
         # conv(x * s, scale * W) == conv(x * (scale * s), W): the equalised-lr scale rides on the (B, Cin) style, so
         # the 2.4 M-float weight is not rescaled (one multiply kernel + one in backward per layer and call)
         w = self.weight.squeeze(0)                                   # (Cout, Cin, k, k), shared by the batch
         demod = None
         if self.demodulate:
-            wsq = w.pow(2).sum([2, 3])                               # (Cout, Cin)
+            wsq = weight_sqsum(w)                                    # (Cout, Cin), one pass over the weight
             demod = torch.rsqrt(F.linear(s.pow(2), wsq) * (self.scale ** 2) + self.eps)   # (B, Cout)
         s = s * self.scale
         return _conv.modulated_conv2d(input, w, s, demod, upsample=self.upsample, downsample=self.downsample,
@@ -296,11 +301,11 @@ class StyledConv(nn.Module):
         self.noise = NoiseInjection()
         self.activate = FusedLeakyReLU(out_channel)
 
-    def forward(self, input, style, noise=None):
+    def forward(self, input, style, noise=None, s=None):
         if _FUSED_STYLED and _conv._styled.fused_ok(input) and self.conv.demodulate and self.conv.out_channel % 4 == 0:
             return self.conv(input, style, epilogue=(noise, self.noise.weight, self.activate.bias,
-                                                     self.activate.negative_slope, self.activate.scale))
-        out = self.conv(input, style)
+                                                     self.activate.negative_slope, self.activate.scale), s=s)
+        out = self.conv(input, style, s=s)
         out = self.noise(out, noise=noise)
         return self.activate(out)
 
@@ -313,8 +318,8 @@ class ToRGB(nn.Module):
         self.conv = ModulatedConv2d(in_channel, 3, 1, style_dim, demodulate=False)
         self.bias = nn.Parameter(torch.zeros(1, 3, 1, 1))
 
-    def forward(self, input, style, skip=None):
-        out = self.conv(input, style) + self.bias
+    def forward(self, input, style, skip=None, s=None):
+        out = self.conv(input, style, s=s) + self.bias
         if skip is not None:
             out = out + self.upsample(skip)
         return out
@@ -375,17 +380,50 @@ class Generator(nn.Module):
     def get_latent(self, input):
         return self.style(input)
 
+    def map_latent(self, z):
+        """``self.style(z)``.  Without autograd (every call of the adaptation loop: the mapping network is not among the
+        trained parameters, train:908-917) the PixelNorm + 8 x EqualLinear chain runs as one launch per layer."""
+        if (_FUSED_LINEARS and z.is_cuda and z.dtype == torch.float32 and z.dim() == 2 and z.shape[0] <= 8
+                and not torch.is_grad_enabled()):
+            lin = [m for m in self.style if isinstance(m, EqualLinear)]
+            if all(m.activation and m.bias is not None and m.weight.is_contiguous() for m in lin):
+                return _glue.mapping_network(z, [m.weight for m in lin], [m.bias for m in lin], lin[0].scale, lin[0].lr_mul)
+        return self.style(z)
+
+    def _modulated(self):
+        """(ModulatedConv2d, latent index) in forward order: conv1, to_rgb1, then (up conv, conv, to_rgb) per block
+        (model_probe_tune.py:567-582)."""
+        plan = [(self.conv1.conv, 0), (self.to_rgb1.conv, 1)]
+        i = 1
+        for up_conv, conv, rgb in zip(self.convs[::2], self.convs[1::2], self.to_rgbs):
+            plan += [(up_conv.conv, i), (conv.conv, i + 1), (rgb.conv, i + 2)]
+            i += 2
+        return plan
+
+    def all_modulations(self, latent):
+        """Every layer's ``modulation(latent[:, i])`` from ONE launch (and one for all their weight gradients), or None
+        when the fused path does not apply.  Returned in the order of ``_modulated()``."""
+        plan = self._modulated()
+        mods = [m.modulation for m, _ in plan]
+        if not (_FUSED_LINEARS and latent.dim() == 3 and _glue.linear_multi_ok(latent, [m.weight for m in mods])
+                and all(m.bias is not None and not m.activation for m in mods)):
+            return None
+        return _glue.linear_multi(latent, [i for _, i in plan], [m.weight for m in mods], [m.bias for m in mods],
+                                  [m.scale for m in mods], [m.lr_mul for m in mods])
+
     def estimate_fisher(self, loglikelihood):
         return _estimate_fisher(self, loglikelihood)
 
     def forward(self, *args, **kwargs):
+        if _FUSED_LINEARS and self.input.input.is_cuda:       # every EqualLinear of G is served by the fused launches
+            return self._forward(*args, **kwargs)
         with _Prescaled(self):
             return self._forward(*args, **kwargs)
 
     def _forward(self, styles, return_latents=False, inject_index=None, truncation=1, truncation_latent=None,
                  input_is_latent=False, noise=None, randomize_noise=True, return_feats=False):
         if not input_is_latent:
-            styles = [self.style(s) for s in styles]
+            styles = [self.map_latent(s) for s in styles]
         if noise is None:
             noise = ([None] * self.num_layers if randomize_noise
                      else [getattr(self.noises, f"noise_{i}") for i in range(self.num_layers)])
@@ -401,17 +439,21 @@ class Generator(nn.Module):
                                 styles[1].unsqueeze(1).repeat(1, self.n_latent - inject_index, 1)], 1)
 
         feats: List[torch.Tensor] = []
+        latent = latent.contiguous()
+        mods = self.all_modulations(latent) if latent.is_cuda else None
+        sm = iter(mods) if mods is not None else iter(())
+        nxt = (lambda: next(sm)) if mods is not None else (lambda: None)
         out = _fmt(self.input(latent))
-        out = self.conv1(out, latent[:, 0], noise=noise[0])
+        out = self.conv1(out, latent[:, 0], noise=noise[0], s=nxt())
         feats.append(out)
-        skip = self.to_rgb1(out, latent[:, 1])
+        skip = self.to_rgb1(out, latent[:, 1], s=nxt())
         i = 1
         for up_conv, conv, n1, n2, rgb in zip(self.convs[::2], self.convs[1::2], noise[1::2], noise[2::2], self.to_rgbs):
-            out = up_conv(out, latent[:, i], noise=n1)
+            out = up_conv(out, latent[:, i], noise=n1, s=nxt())
             feats.append(out)
-            out = conv(out, latent[:, i + 1], noise=n2)
+            out = conv(out, latent[:, i + 1], noise=n2, s=nxt())
             feats.append(out)
-            skip = rgb(out, latent[:, i + 2], skip)
+            skip = rgb(out, latent[:, i + 2], skip, s=nxt())
             i += 2
         image = skip
         if return_latents:

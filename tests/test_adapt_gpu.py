@@ -250,12 +250,14 @@ def _graphed_vs_oracle(size, iters, cfg, live_oracle=True):
 def _assert_curve_tracks(got, want, keys, what):
     """Stated tolerance for a GAN loss curve under TF32 convolutions with Adam beta1 = 0 (every first update is
     lr * sign(grad), so rounding-level gradient differences flip individual weight updates and two runs drift apart
-    chaotically): iteration 0 -- before any update has happened -- within 1e-2 relative on every logged loss; every later
-    iteration within 0.05 absolute + 25 % relative on the d / g losses; the curve as a whole within 10 % mean relative
-    deviation."""
+    chaotically): the d loss of iteration 0 -- computed before any update has happened -- within 1e-2 relative, the other
+    losses of iteration 0 (g, r1, path: after the first D / G updates) within 5 %; every iteration within 0.05 absolute +
+    25 % relative on the d / g losses; the curve as a whole within 10 % mean relative deviation.  Measured in round 2 at
+    256 px over 50 iterations: mean 2.7 %, worst single entry 22 %."""
     print(f"{what}: columns {list(keys)}\noracle\n{np.array2string(want, precision=4)}\ngpu\n{np.array2string(got, precision=4)}")
     assert np.array_equal(np.isnan(got), np.isnan(want)), "the two runs logged different losses"
-    np.testing.assert_allclose(got[0], want[0], rtol=1e-2, atol=1e-2, err_msg="iteration 0")
+    np.testing.assert_allclose(got[0, 0], want[0, 0], rtol=1e-2, atol=1e-2, err_msg="iteration 0, d loss")
+    np.testing.assert_allclose(got[0], want[0], rtol=5e-2, atol=1e-2, err_msg="iteration 0")
     dg = [list(keys).index("d"), list(keys).index("g")]
     np.testing.assert_allclose(got[:, dg], want[:, dg], rtol=0.25, atol=5e-2)
     rel = np.abs(got[:, dg] - want[:, dg]) / np.maximum(np.abs(want[:, dg]), 0.05)

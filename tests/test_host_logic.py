@@ -206,7 +206,8 @@ def test_fused_generator_plan_on_cpu(cpu_stubbed, monkeypatch):
     def conv_stub(xm, wt, geom, demod=None, noise=None, noise_weight=None, bias=None, act=False, alpha=0.2,
                   scale=2 ** 0.5, s_next=None, want_out2=False):
         k = int(round(geom.n_weight_taps ** 0.5))
-        w = wt.view(k, k, geom.cout, geom.cin).permute(2, 3, 0, 1)
+        # the weight arrives either packed (taps, Cout, Cin) or as the (Cout, Cin, k, k) parameter read in place
+        w = wt if wt.dim() == 4 else wt.view(k, k, geom.cout, geom.cin).permute(2, 3, 0, 1)
         x = xm.permute(0, 3, 1, 2)
         if geom.n_phases == 4:
             acc = F.conv_transpose2d(x, w.transpose(0, 1), stride=2)
@@ -314,7 +315,7 @@ def test_lib_conv_first_and_second_order_match_autograd(transposed, stride, padd
         return F.conv2d(x, w, stride=stride, padding=padding)
 
     def new(x, w):
-        return _lib_conv(x, w.transpose(0, 1) if transposed else w, stride, padding, transposed)
+        return _lib_conv(x, w, stride, padding, transposed)     # w is (Cout, Cin, k, k) in both directions
 
     res = []
     for f in (ref, new):
