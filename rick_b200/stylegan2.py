@@ -401,15 +401,26 @@ class Generator(nn.Module):
         return plan
 
     def all_modulations(self, latent):
-        """Every layer's ``modulation(latent[:, i])`` from ONE launch (and one for all their weight gradients), or None
-        when the fused path does not apply.  Returned in the order of ``_modulated()``."""
+        """Every layer's ``modulation(latent[:, i])`` from TWO launches -- the StyledConv layers and the ToRGB layers --
+        (and one each for their weight gradients), or None when the fused path does not apply.  Returned in the order
+        of ``_modulated()``.  Two autograd nodes, not one: the adaptation loop trains the StyledConv modulations but not
+        the ToRGB ones (train:908-917), and with a single node a backward restricted to the trained subset would still
+        have to produce d loss / d s of every ToRGB -- a (3 x Cin) x 65536-pixel weight-gradient GEMM per layer that
+        the restricted backward otherwise prunes (1.9 ms per iteration when it was not)."""
         plan = self._modulated()
         mods = [m.modulation for m, _ in plan]
         if not (_FUSED_LINEARS and latent.dim() == 3 and _glue.linear_multi_ok(latent, [m.weight for m in mods])
                 and all(m.bias is not None and not m.activation for m in mods)):
             return None
-        return _glue.linear_multi(latent, [i for _, i in plan], [m.weight for m in mods], [m.bias for m in mods],
-                                  [m.scale for m in mods], [m.lr_mul for m in mods])
+        out = [None] * len(plan)
+        for want_rgb in (False, True):
+            sel = [k for k, (m, _) in enumerate(plan) if (m.out_channel == 3 and m.kernel_size == 1) == want_rgb]
+            res = _glue.linear_multi(latent, [plan[k][1] for k in sel], [mods[k].weight for k in sel],
+                                     [mods[k].bias for k in sel], [mods[k].scale for k in sel],
+                                     [mods[k].lr_mul for k in sel])
+            for k, r in zip(sel, res):
+                out[k] = r
+        return out
 
     def estimate_fisher(self, loglikelihood):
         return _estimate_fisher(self, loglikelihood)

@@ -152,8 +152,10 @@ def test_graphed_adapter_replays_the_eager_iteration_and_fisher_round():
         return G.cuda(), D.cuda(), Ge.cuda(), De.cuda()
 
     class Det(GraphedRickAdapter):                        # latents come from buffers the test fills
-        def _latent(self, batch, key):
-            return self.g.style(self._z[key][:batch]).unsqueeze(1).repeat(1, self.g.n_latent, 1)
+        def _latent(self, batch, key):            # same arithmetic as RickAdapter._latents (fused mapping network)
+            with torch.no_grad():
+                lat = self.g.map_latent(self._z[key][:batch]).unsqueeze(1).repeat(1, self.g.n_latent, 1)
+            return lat
 
     eager = RickAdapter(cfg, *nets())
     graphed = Det(cfg, *nets(), fused_generator=False)    # same generator executor as the eager adapter
