@@ -323,6 +323,15 @@ RICK_API int rick_linear_multi(float* const* y, const float* const* w, const flo
                                const int64_t* x_stride, const int* out_dim, const float* w_scale, const float* b_scale,
                                int count, int batch, int in_dim, int act, float alpha, float act_scale, int pixelnorm,
                                rick_stream_t stream);
+/* The discriminator's from-RGB layer, ConvLayer(3, C, 1) = 1x1 EqualConv2d + FusedLeakyReLU (model_probe_tune.py:595-641,
+ * 676), as one pass each way.  img / gimg are NCHW (batch, cin <= 4, pixels), y / g NHWC (batch, pixels, cout), w (cout, cin).
+ *   fwd       y = act( w_scale * sum_c img[c] * w[co,c] + bias[co] )        act != 0: leaky-ReLU(alpha) * act_scale
+ *   bwd_data  gimg[c] = w_scale * sum_co w[co,c] * t[co],   t = act != 0 ? (y > 0 ? g : alpha*g) * act_scale : g */
+RICK_API int rick_from_rgb_fwd(float* y, const float* img, const float* w, const float* bias, int batch, int64_t pixels,
+                               int cin, int cout, float w_scale, int act, float alpha, float act_scale, rick_stream_t stream);
+RICK_API int rick_from_rgb_bwd_data(float* gimg, const float* g, const float* y, const float* w, int batch, int64_t pixels,
+                                    int cin, int cout, float w_scale, int act, float alpha, float act_scale,
+                                    rick_stream_t stream);
 RICK_API int rick_linear_multi_wgrad(float* const* gw, float* const* gbias, const float* const* gy, const float* const* x,
                                      const int64_t* x_stride, const int* out_dim, const float* w_scale,
                                      const float* b_scale, int count, int batch, int in_dim, rick_stream_t stream);

@@ -55,6 +55,10 @@ _PROTOTYPES = {
                                   POINTER(c_float), c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p]),
     "rick_linear_multi_wgrad": (c_int, [POINTER(c_void_p)] * 4 + [POINTER(c_int64), POINTER(c_int), POINTER(c_float),
                                         POINTER(c_float), c_int, c_int, c_int, c_void_p]),
+    "rick_from_rgb_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_float, c_int,
+                                  c_float, c_float, c_void_p]),
+    "rick_from_rgb_bwd_data": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_float,
+                                       c_int, c_float, c_float, c_void_p]),
     "rick_weight_sqsum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_void_p]),
     "rick_adam_mask_ema": (c_int, [POINTER(c_void_p)] * 8 + [POINTER(c_int64), POINTER(c_int64), c_int,
                                    c_float, c_float, c_float, c_float, c_float, c_void_p]),

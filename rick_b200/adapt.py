@@ -243,9 +243,20 @@ class RickAdapter:
         return torch.cat([w[0].unsqueeze(1).repeat(1, inject, 1), w[1].unsqueeze(1).repeat(1, n - inject, 1)], 1)
 
     def _gate_warmup(self, i: int):
-        warm = i < self.cfg.warmup_iter
+        self._warm = i < self.cfg.warmup_iter
+
+    def _grad_mode(self, net: str):
+        """``requires_grad(generator, net == "g"); requires_grad(discriminator, net == "d")`` (train:396-398, 497-499),
+        narrowed to the parameters the optimisers own (train:908-931): a network's other parameters never need a
+        gradient inside the loop, and switching the OTHER network off keeps the custom convolution / bias-act Functions
+        from computing weight gradients nobody reads (the G step back-propagates through D for its data gradients only).
+        During warm-up only D's ``final_*`` parameters train (train:202-211)."""
+        warm = getattr(self, "_warm", False)
+        train_g, train_d = {id(p) for p in self.g_train}, {id(p) for p in self.d_train}
+        for n, p in self.g_named.items():
+            p.requires_grad_(net == "g" and id(p) in train_g)
         for n, p in self.d_named.items():
-            p.requires_grad_((not warm) or ("final" in n))
+            p.requires_grad_(net == "d" and id(p) in train_d and ((not warm) or "final" in n))
 
     def step(self, i: int, real_img: torch.Tensor, draws: DrawStream, explicit_layer_noise: bool = False
              ) -> Dict[str, torch.Tensor]:
@@ -263,6 +274,7 @@ class RickAdapter:
             lat = self._latents(z, inject)
             gen = self.fg if self.fg is not None else self.g     # fg reads G's parameters in place: always current
             fake_img, _ = gen([lat], input_is_latent=True, noise=noise_of(cfg.batch))
+        self._grad_mode("d")
         fake_pred, real_pred = d_pair(self.d, fake_img, real_img)
         d_loss = d_logistic_loss(real_pred, fake_pred)
         out["d"], out["real_score"], out["fake_score"] = d_loss.detach(), real_pred.mean().detach(), fake_pred.mean().detach()
@@ -293,6 +305,7 @@ class RickAdapter:
         # ---- G step (train:500-540) ----
         z = draws.mixing_latents(cfg.batch, cfg.latent, cfg.mixing)
         inject = draws.randint(1, self.g.n_latent - 1) if len(z) == 2 else None
+        self._grad_mode("g")
         if after_warmup:
             fake_img, _ = self.g([self._latents(z, inject)], input_is_latent=True, noise=noise_of(cfg.batch))
             fake_pred, _ = self.d(fake_img)

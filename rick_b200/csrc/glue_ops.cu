@@ -216,3 +216,122 @@ extern "C" int rick_linear_multi_wgrad(float* const* gw, float* const* gbias, co
     }
     return RICK_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// The discriminator's from-RGB layer: ConvLayer(3, C, 1) = EqualConv2d 1x1 (no bias) + FusedLeakyReLU
+// (model_probe_tune.py:595-641, 676).  With K = 3 input channels it is an outer product per pixel, not a GEMM: as
+// library / element-wise calls it cost 3 broadcast multiplies, 2 adds, a layout copy and the bias-act pass over the
+// (B, C, 256, 256) output (0.55 ms at batch 4), and its data gradient three more broadcast multiply + reduce pairs.
+//
+//   from_rgb_fwd      y[b,p,co] = lrelu( w_scale * sum_c img[b,c,p] * w[co,c] + bias[co] ) * act_scale       (NCHW -> NHWC)
+//   from_rgb_bwd_data gimg[b,c,p] = w_scale * sum_co w[co,c] * t[b,p,co],  t = (y > 0 ? g : alpha*g) * act_scale
+//
+// Both are one pass over the feature map (write-bound / read-bound).
+namespace rick {
+namespace {
+
+__global__ void __launch_bounds__(256)
+from_rgb_fwd_kernel(float* __restrict__ y, const float* __restrict__ img, const float* __restrict__ w,
+                    const float* __restrict__ bias, long long pixels_per_sample, int batch, int cin, int cout, float w_scale,
+                    int act, float alpha, float act_scale) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long total = pixels_per_sample * batch;
+    for (int cq = lane * 4; cq < cout; cq += 128) {           // this lane's 4 output channels (cout % 4 == 0)
+        float wr[4][4];
+        float br[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            br[j] = bias ? __ldg(bias + cq + j) : 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) wr[j][c] = c < cin ? __ldg(w + (long long)(cq + j) * cin + c) * w_scale : 0.f;
+        }
+        for (long long p = warp; p < total; p += n_warps) {
+            const long long b = p / pixels_per_sample, q = p - b * pixels_per_sample;
+            const float* src = img + b * cin * pixels_per_sample + q;
+            float x[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) x[c] = c < cin ? __ldg(src + c * pixels_per_sample) : 0.f;
+            float4 o;
+            float* op = reinterpret_cast<float*>(&o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float v = fmaf(x[0], wr[j][0], fmaf(x[1], wr[j][1], fmaf(x[2], wr[j][2], fmaf(x[3], wr[j][3], br[j]))));
+                if (act) v = (v > 0.f ? v : v * alpha) * act_scale;
+                op[j] = v;
+            }
+            st_stream_f4(reinterpret_cast<float4*>(y + p * cout + cq), o);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+from_rgb_bwd_data_kernel(float* __restrict__ gimg, const float* __restrict__ g, const float* __restrict__ y,
+                         const float* __restrict__ w, long long pixels_per_sample, int batch, int cin, int cout,
+                         float w_scale, int act, float alpha, float act_scale) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long total = pixels_per_sample * batch;
+    for (long long p = warp; p < total; p += n_warps) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int cq = lane * 4; cq < cout; cq += 128) {
+            const float4 gv = ld_stream_f4(reinterpret_cast<const float4*>(g + p * cout + cq));
+            float t[4] = {gv.x, gv.y, gv.z, gv.w};
+            if (act) {
+                const float4 yv = ld_stream_f4(reinterpret_cast<const float4*>(y + p * cout + cq));
+                const float ys[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) t[j] = (ys[j] > 0.f ? t[j] : t[j] * alpha) * act_scale;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c < cin) acc[c] = fmaf(t[j], __ldg(w + (long long)(cq + j) * cin + c), acc[c]);
+        }
+        const long long b = p / pixels_per_sample, q = p - b * pixels_per_sample;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (c < cin) {
+                const float s = warp_sum(acc[c]);
+                if (lane == 0) gimg[(b * cin + c) * pixels_per_sample + q] = s * w_scale;
+            }
+        }
+    }
+}
+
+}  // namespace
+}  // namespace rick
+
+extern "C" int rick_from_rgb_fwd(float* y, const float* img, const float* w, const float* bias, int batch, int64_t pixels,
+                                 int cin, int cout, float w_scale, int act, float alpha, float act_scale,
+                                 rick_stream_t stream) {
+    using namespace rick;
+    if (!y || !img || !w || batch < 1 || pixels < 1) return RICK_ERR_INVALID_ARGUMENT;
+    if (cin < 1 || cin > 4 || cout < 4 || cout % 4 != 0) return RICK_ERR_UNSUPPORTED;
+    if (!aligned_to(y, 16)) return RICK_ERR_ALIGNMENT;
+    long long blocks = ceil_div(pixels * batch, 8 * 4);       // a warp handles ~4 pixels
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    from_rgb_fwd_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(y, img, w, bias, pixels, batch, cin,
+                                                                                          cout, w_scale, act, alpha, act_scale);
+    RICK_CHECK_LAUNCH();
+    return RICK_OK;
+}
+
+extern "C" int rick_from_rgb_bwd_data(float* gimg, const float* g, const float* y, const float* w, int batch, int64_t pixels,
+                                      int cin, int cout, float w_scale, int act, float alpha, float act_scale,
+                                      rick_stream_t stream) {
+    using namespace rick;
+    if (!gimg || !g || !w || (act && !y) || batch < 1 || pixels < 1) return RICK_ERR_INVALID_ARGUMENT;
+    if (cin < 1 || cin > 4 || cout < 4 || cout % 4 != 0) return RICK_ERR_UNSUPPORTED;
+    if (!aligned_to(g, 16) || (y && !aligned_to(y, 16))) return RICK_ERR_ALIGNMENT;
+    long long blocks = ceil_div(pixels * batch, 8 * 4);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    from_rgb_bwd_data_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(gimg, g, y, w, pixels, batch, cin,
+                                                                                               cout, w_scale, act, alpha,
+                                                                                               act_scale);
+    RICK_CHECK_LAUNCH();
+    return RICK_OK;
+}

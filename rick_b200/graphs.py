@@ -80,8 +80,7 @@ class GraphedRickAdapter(RickAdapter):
         self._outs: Dict[str, Dict[str, torch.Tensor]] = {}
         self._graph_launches: Dict[str, int] = {}      # rick_b200 kernel nodes recorded in each graph
         self.replayed_launches = 0                      # rick_b200 kernels executed through graph replays so far
-        for p in list(generator.parameters()) + list(discriminator.parameters()):
-            p.requires_grad_(True)
+        self._warm = False
 
     # ---- graph bodies -----------------------------------------------------------------------------------
     def _latent(self, batch: int, key: str) -> torch.Tensor:
@@ -104,6 +103,7 @@ class GraphedRickAdapter(RickAdapter):
                 fake_img, _ = self.fg([latent], input_is_latent=True, noise=self._layer_noise("d"))
             else:
                 fake_img, _ = self.g([latent], input_is_latent=True, noise=self._layer_noise("d"))
+        self._grad_mode("d")
         fake_pred, real_pred = d_pair(self.d, fake_img, self._real)
         d_loss = d_logistic_loss(real_pred, fake_pred)
         self.d.zero_grad(set_to_none=True)
@@ -114,6 +114,7 @@ class GraphedRickAdapter(RickAdapter):
 
     def _body_r1(self):
         cfg = self.cfg
+        self._grad_mode("d")
         real_r = self._real.detach().clone().requires_grad_(True)
         real_pred, _ = self.d(real_r)
         real_pred = real_pred.view(real_r.size(0), -1).mean(dim=1).unsqueeze(1)
@@ -126,6 +127,7 @@ class GraphedRickAdapter(RickAdapter):
 
     def _body_g(self):
         cfg = self.cfg
+        self._grad_mode("g")
         latent = self._latent(cfg.batch, "g")
         fake_img, _ = self.g([latent], input_is_latent=True, noise=self._layer_noise("g"))
         fake_pred, _ = self.d(fake_img)
@@ -139,6 +141,7 @@ class GraphedRickAdapter(RickAdapter):
     def _body_path(self):
         cfg = self.cfg
         pb = max(1, cfg.batch // cfg.path_batch_shrink)
+        self._grad_mode("g")
         latent = self._latent(pb, "path").requires_grad_(True)
         fake_img, latents = self.g([latent], input_is_latent=True, return_latents=True, noise=self._layer_noise("path"))
         path_noise = self._path_noise if self.explicit_inputs else torch.randn_like(fake_img)

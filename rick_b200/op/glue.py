@@ -165,3 +165,61 @@ def mapping_network(z: torch.Tensor, weights: Sequence[torch.Tensor], biases: Se
         (y,) = _linear_multi_launch(x, [0], [w], [bb], [w_scale], [b_scale], True, negative_slope, act_scale, i == 0)
         x = y.unsqueeze(1)
     return x.squeeze(1)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the discriminator's from-RGB layer (1x1 conv from <= 4 channels + bias + leaky-ReLU) in one pass each way
+# ---------------------------------------------------------------------------------------------------------------
+class _FromRGB(Function):
+    @staticmethod
+    def forward(ctx, img, weight, bias, w_scale, alpha, act_scale):
+        b, cin, h, w = img.shape
+        cout = weight.shape[0]
+        img_c = img.contiguous()
+        w2 = weight.reshape(cout, cin).contiguous()
+        y = torch.empty((b, h, w, cout), dtype=torch.float32, device=img.device)
+        with torch.cuda.device(img.device):
+            _lib.check(_lib.lib().rick_from_rgb_fwd(y.data_ptr(), img_c.data_ptr(), w2.data_ptr(),
+                                                    None if bias is None else bias.data_ptr(), b, h * w, cin, cout,
+                                                    float(w_scale), 1, float(alpha), float(act_scale), _stream()),
+                       "rick_from_rgb_fwd")
+        ctx.save_for_backward(img_c, weight, y)
+        ctx.cfg = (float(w_scale), float(alpha), float(act_scale), bias is not None)
+        return y.permute(0, 3, 1, 2)                       # logical NCHW, channels-last memory
+
+    @staticmethod
+    def backward(ctx, g):
+        img, weight, y = ctx.saved_tensors
+        w_scale, alpha, act_scale, has_bias = ctx.cfg
+        need_img, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2] and has_bias
+        b, cin, h, w = img.shape
+        cout = weight.shape[0]
+        w2 = weight.reshape(cout, cin)
+        if torch.is_grad_enabled() or need_w or need_b:
+            # create_graph (R1 differentiates d D / d image again) or parameter gradients (Fisher round only: the layer
+            # is not among the trained parameters, train:921-931): differentiable formulas
+            t = torch.where(y > 0, g.permute(0, 2, 3, 1), g.permute(0, 2, 3, 1) * alpha) * act_scale      # (B, H, W, Co)
+            g_img = torch.einsum("bhwo,oc->bchw", t, w2) * w_scale if need_img else None
+            g_w = (torch.einsum("bhwo,bchw->oc", t, img) * w_scale).reshape(weight.shape) if need_w else None
+            g_b = t.sum((0, 1, 2)) if need_b else None
+            return g_img, g_w, g_b, None, None, None
+        g_img = None
+        if need_img:
+            gc = g.permute(0, 2, 3, 1).contiguous()         # a view when g is channels-last
+            g_img = torch.empty_like(img)
+            with torch.cuda.device(img.device):
+                _lib.check(_lib.lib().rick_from_rgb_bwd_data(g_img.data_ptr(), gc.data_ptr(), y.data_ptr(),
+                                                             w2.contiguous().data_ptr(), b, h * w, cin, cout, w_scale, 1,
+                                                             alpha, act_scale, _stream()), "rick_from_rgb_bwd_data")
+        return g_img, None, None, None, None, None
+
+
+def from_rgb_ok(img: torch.Tensor, weight: torch.Tensor) -> bool:
+    return (img.is_cuda and img.dtype == torch.float32 and img.dim() == 4 and weight.dim() == 4 and weight.shape[1] <= 4
+            and weight.shape[2] == weight.shape[3] == 1 and weight.shape[0] % 4 == 0 and img.shape[1] == weight.shape[1])
+
+
+def from_rgb(img, weight, bias, w_scale: float, negative_slope: float = 0.2, act_scale: float = 2 ** 0.5):
+    """``fused_leaky_relu(conv2d(img, weight * w_scale), bias)`` for a 1x1 convolution from <= 4 channels; the result is a
+    logical (B, Cout, H, W) tensor in channels-last memory."""
+    return _FromRGB.apply(img, weight, bias, w_scale, negative_slope, act_scale)

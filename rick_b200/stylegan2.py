@@ -534,11 +534,20 @@ class Discriminator(nn.Module):
         with _Prescaled(self):
             return self._forward(*args, **kwargs)
 
+    def _from_rgb(self, inp):
+        """``self.convs[0]``: ConvLayer(3, C, 1) = 1x1 EqualConv2d + FusedLeakyReLU, as one fused pass when possible."""
+        layer = self.convs[0]
+        conv, act = layer[0], layer[1] if len(layer) > 1 else None
+        if (_CHANNELS_LAST and isinstance(conv, EqualConv2d) and isinstance(act, FusedLeakyReLU) and conv.bias is None
+                and conv.stride == 1 and conv.padding == 0 and _glue.from_rgb_ok(inp, conv.weight)):
+            return _glue.from_rgb(inp, conv.weight, act.bias, conv.scale, act.negative_slope, act.scale)
+        return layer(_fmt(inp))
+
     def _forward(self, inp, ind=None, real=False, stddev_group=None):
         """``stddev_group``: override of ``min(batch, self.stddev_group)`` for the minibatch-stddev grouping -- used by
         rick_b200.adapt.d_pair to score two batches in one pass with each batch's own statistics."""
         feat: list = []
-        out = self.convs[0](_fmt(inp))
+        out = self._from_rgb(inp)
         feat.append(out)
         for block in list(self.convs)[1:]:
             out = block(out, feat)          # conv1 / conv2 evaluated ONCE (see module docstring)

@@ -437,3 +437,40 @@ def test_mapping_network_fused_forward():
         got = G.map_latent(z)
     want = G.style(z)                                           # autograd on: the module path
     torch.testing.assert_close(got, want.detach(), rtol=1e-4, atol=1e-5)
+
+
+def test_from_rgb_fused_layer_matches_modules_to_second_order():
+    """D's from-RGB ConvLayer as one fused pass each way: value, d/d image (kernel path), parameter gradients and the
+    R1-style second derivative (composite path) against the EqualConv2d + FusedLeakyReLU modules it replaces."""
+    from rick_b200 import stylegan2 as sg
+    from rick_b200.op import glue
+    torch.manual_seed(0)
+    layer = sg.ConvLayer(3, 128, 1).cuda()
+    layer[1].bias.data.normal_()
+    conv, act = layer[0], layer[1]
+    img = torch.randn(2, 3, 24, 20, device="cuda")
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        def fused(x):
+            return glue.from_rgb(x, conv.weight, act.bias, conv.scale, act.negative_slope, act.scale)
+
+        def modular(x):
+            return layer(x)
+
+        res = []
+        for fn in (fused, modular):
+            x = img.clone().requires_grad_(True)
+            y = fn(x)
+            go = torch.randn(2, 128, 24, 20, generator=torch.Generator().manual_seed(1)).cuda()
+            (gx,) = torch.autograd.grad(y, x, go)                                           # first order, no graph
+            x2 = img.clone().requires_grad_(True)
+            y2 = fn(x2)
+            gx2, gw, gb = torch.autograd.grad((y2 * go).sum(), [x2, conv.weight, act.bias], create_graph=True)
+            (ggw,) = torch.autograd.grad(gx2.pow(2).sum(), conv.weight)                    # R1 pattern
+            res.append((y.detach(), gx, gx2.detach(), gw.detach(), gb.detach(), ggw))
+        assert res[0][0].is_contiguous(memory_format=torch.channels_last)
+        for name, a, b in zip(("y", "gx", "gx (graph)", "gw", "gb", "d|gx|^2/dw"), *res):
+            torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5, msg=name)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
