@@ -14,12 +14,16 @@ line says how many Fisher / R1 / path-length iterations were inside the timed re
   e2e     the same loop through the public API with HOST inputs: every step copies its real images from pinned host
           memory and reads the step's losses back to the host
   N > 1   one process per GPU (torchrun), DDP-style gradient all-reduce over NCCL, per-GPU batch 2 (weak scaling);
-          value = N x (iterations/s), i.e. batch-2 iteration equivalents per second over the whole job
-  roofline  the tcgen05 modulated convolution (conv_tc_kernel, 64x64 512->512 layer at the sample-generation batch):
-            TF32 flops / launch time against bf16_tflops / 2 of MEASURED_PEAKS.json; ``rooflines`` adds the memory-bound
-            headline kernel (upfirdn2d, BASELINE configs[3] shape (32,512,128,128)->256^2) against hbm_gbs.  Both are
-            timed with CUDA events on the launching stream, L2 flushed between launches; extra.op_sweep holds the rest
-            of configs[3] (blur / down / bias-act / optimiser step, fp32 and bf16)
+          value = N x (optimiser iterations/s): every rank runs its own batch-2 iteration, so this is batch-2
+          iterations processed per second over the whole job (``optimizer_iterations_per_s`` is the un-multiplied rate)
+  roofline  the dominant kernel of the TIMED step, conv_tc_kernel (forward + data-gradient convolutions: 29 % of the
+            iteration's kernel time in profiles/r02*_launches.md): the algorithmic TF32 flops of all its launches in one
+            plain adaptation iteration / the sum of their durations, each launch timed live with CUDA events on the
+            launching stream (L2 flushed between launches), against the TF32 matmul peak MEASURED IN THIS RUN (cuBLAS
+            8192^3, burst).  ``roofline.step`` is the whole iteration: algorithmic conv flops per iteration / ms_per_step.
+            ``rooflines`` adds the weight-gradient kernel, the sample-generation shape (b64 64x64 512->512) and the
+            memory-bound headline kernel (upfirdn2d, BASELINE configs[3] shape) against hbm_gbs; extra.conv_vs_cudnn
+            times every layer shape on cuDNN TF32 as well (SURVEY 2a's bar); extra.op_sweep is all of configs[3]
   cpu_baseline / --impl reference   the oracle port of the same iteration on the box's host cores (the reference's
           CPU path: upfirdn2d_native + native leaky-ReLU semantics), bounded sample
 """
@@ -105,6 +109,29 @@ def load_peaks():
         d = json.load(open(p))
         return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "source": "measured (MEASURED_PEAKS.json)"}
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def measure_tf32_peak(device, n=8192, reps=10):
+    """Dense TF32 matmul throughput of THIS GPU, measured like MEASURED_PEAKS.json's bf16 entry (torch.matmul n^3, best
+    of ``reps``, CUDA events): the denominator of every tensor-bound fraction below."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.randn(n, n, device=device)
+        b = torch.randn(n, n, device=device)
+        for _ in range(3):
+            a @ b
+        best = float("inf")
+        for _ in range(reps):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            a @ b
+            e.record()
+            e.synchronize()
+            best = min(best, s.elapsed_time(e))
+        return 2.0 * n ** 3 / (best / 1e3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
 
 
 def build_networks(size, device, seed=1):
@@ -194,14 +221,11 @@ def run_ours(args):
 
     W, K = args.warmup, args.steps
     try:
-        for i in range(W):
-            iteration(i, False)
-        if mode == "graphs":                      # make sure every graph exists before the timed region
+        if mode == "graphs":                      # capture every graph before iteration 0
             adapter._real.copy_(shots_dev[:batch])
             adapter.prepare()                     # capture leaves weights / optimiser state / RNG untouched
-            # graph capture empties the caching allocator (torch.cuda.graph does gc + empty_cache): let the eager
-            # Fisher round re-acquire its working set once here, as part of the warm-up, not inside the timed steps
-            adapter.fisher_round(fisher_lat, shots_dev[:cfg.num_fisher_img])
+        for i in range(W):
+            iteration(i, False)
     except Exception as exc:                       # graph capture refused: fall back to the eager executor, say so
         if mode != "graphs" or args.mode == "graphs":
             raise
@@ -226,10 +250,13 @@ def run_ours(args):
     e2e_value = world * K / (ms_e2e / 1e3)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "optimizer_iterations_per_s": K / (ms / 1e3),
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "size": 256, "batch_per_gpu": batch, "global_batch": batch * world,
                    "parallelism": f"dp{world}", "conv_math": "tf32 (fp32 storage, fp32 accumulate)",
+                   "value_is": "rank-iterations per second: N ranks x optimiser iterations/s, each rank on its own "
+                               "batch-2 shots (weak scaling)",
                    "exec_mode": mode,
                    "timing": "inputs regenerated on device every step (fresh latents/noise); activations + weights "
                              "(~1.5 GB/iter) exceed L2",
@@ -241,27 +268,39 @@ def run_ours(args):
         "clocks": clocks,
     }
 
-    if rank == 0 and args.quick:
-        line["extra"] = {}
-    elif rank == 0:
-        up = roofline_upfirdn2d(device)
-        tcr = roofline_conv_tc(device)
-        line["roofline"] = tcr               # dominant rick_b200 kernel of the generator forward (tensor bound)
-        line["rooflines"] = [tcr, up]        # + the memory-bound headline kernel of BASELINE.json's metric
-        line["extra"] = {"op_sweep": op_sweep(device),
-                         "fisher_round_ms": time_fisher_round(adapter, fisher_lat, shots_dev) if world == 1 else None,
-                         "g_samples_per_s_b64_per_gpu": g_samples_per_s(Ge, device, fused=True),
-                         "g_samples_per_s_b64_per_gpu_cudnn_module_path": g_samples_per_s(Ge, device, fused=False)}
-        if world == 1 and not args.no_cpu_baseline and not args.quick:
+    extra = {}
+    # Fisher round (5 images sharded over ranks + one all-reduce of the grad^2 accumulators + masks), every N
+    rdist.barrier()
+    fisher_ms = time_fisher_round(adapter, fisher_lat, shots_dev)
+    if world > 1:
+        t = torch.tensor([fisher_ms], device=device)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        fisher_ms = float(t.item())
+    extra["fisher_round_ms"] = fisher_ms
+    if not args.quick:
+        # BASELINE config 3 as specified: 5000 samples at batch 64, sharded over the ranks (gan_training/eval.py:31-46),
+        # every image copied to host memory, feature statistics all-reduced once at the end
+        from rick_b200 import sample as rsample
+        extra["samplegen_5000"] = rsample.run(Ge, 5000, 64, rank, world, seed=1000, to_host=True, stats=True)
+        extra["samplegen_5000_device_only"] = rsample.run(Ge, 5000, 64, rank, world, seed=1000, to_host=False,
+                                                          stats=False)["samples_per_s"]
+    if rank == 0 and not args.quick:
+        tf32_peak = measure_tf32_peak(device)
+        prof = conv_step_profile(device, tf32_peak, ms / K, with_cudnn=True)
+        line["roofline"] = prof["roofline"]
+        line["rooflines"] = [prof["roofline"], prof["wgrad"], roofline_conv_tc(device, tf32_peak),
+                             roofline_upfirdn2d(device)]
+        extra["conv_vs_cudnn"] = prof["table"]
+        extra["tf32_peak_measured_tflops"] = tf32_peak
+        extra["op_sweep"] = op_sweep(device)
+        extra["g_samples_per_s_b64_per_gpu"] = g_samples_per_s(Ge, device, fused=True)
+        extra["g_samples_per_s_b64_per_gpu_library_conv_module_path"] = g_samples_per_s(Ge, device, fused=False,
+                                                                                       library=True)
+        if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(max_seconds=40.0)
     if world > 1:
-        # sample generation scales by sharding batches with no communication: report the whole-job rate as well
-        sps = g_samples_per_s(Ge, device, batches=4, fused=True)
-        t = torch.tensor([sps], device=device)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
-        if rank == 0:
-            line["extra"]["g_samples_per_s_b64_whole_job"] = float(t.item())
         rdist.barrier()
+    line["extra"] = extra
     if rank == 0:
         emit(line)
     if world > 1:
@@ -425,12 +464,10 @@ def time_fisher_round(adapter, fisher_lat, shots_dev):
     return (time.perf_counter() - t) * 1e3
 
 
-def roofline_conv_tc(device):
+def roofline_conv_tc(device, tf32_peak):
     """rick_conv_tc on the sample-generation shape of the 64x64 layers (batch 64, 512 -> 512, 3x3): TF32 tensor-core
     work 2*B*H*W*Cin*Cout*9 flop per launch, CUDA events on the launching stream, L2 flushed between launches."""
     from rick_b200 import conv_tc as ct
-    peaks = load_peaks()
-    peak = peaks["bf16_tflops"] / 2          # TF32 dense runs at half the bf16 rate; no TF32 entry in MEASURED_PEAKS.json
     b, h, cin, cout = 64, 64, 512, 512
     x = torch.randn(b, h, h, cin, device=device)
     wt = torch.randn(9, cout, cin, device=device) / (cin * 9) ** 0.5
@@ -439,15 +476,117 @@ def roofline_conv_tc(device):
     ms = _time_kernel(lambda: ct.conv_tc_nhwc(x, wt, geom), flush)
     flops = 2 * b * h * h * cin * cout * 9
     achieved = flops / (ms / 1e3) / 1e12
-    return {"kernel": "conv_tc_kernel (3x3, b64 64x64 512->512)", "bound": "tensor", "achieved": achieved, "peak": peak,
-            "unit": "TFLOP/s", "frac": achieved / peak, "traffic": _traffic("conv_tc_kernel (3x3, b64 64x64 512->512)"),
-            "peak_source": peaks["source"] + ": bf16_tflops / 2 (tf32)", "ms_per_launch": ms, "algorithmic_flops": flops}
+    return {"kernel": "conv_tc_kernel (3x3, b64 64x64 512->512: the sample-generation shape)", "bound": "tensor",
+            "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
+            "traffic": _traffic("conv_tc_kernel (3x3, b64 64x64 512->512)"),
+            "peak_source": "measured in this run: torch.matmul TF32 8192^3, best of 10", "ms_per_launch": ms,
+            "algorithmic_flops": flops}
+
+
+# Convolution launches of ONE plain adaptation iteration (256 px, batch 2): (name, B, H, W, Cin, Cout, k, stride, pad,
+# transposed, primitives).  D step: G forward on the tcgen05 executor (no grad), D on the joint fake+real batch of 4 with
+# forward / data gradient (not into the image) / weight gradient.  G step: G forward, D forward, data gradients through D
+# and G, weight gradients of G's trained layers.
+def _iteration_convs():
+    d = [("conv1 256", 256, 256, 128, 128, 3, 1, 1), ("conv2 256>128", 257, 257, 128, 256, 3, 2, 0),
+         ("skip 256>128", 255, 255, 128, 256, 1, 2, 0), ("conv1 128", 128, 128, 256, 256, 3, 1, 1),
+         ("conv2 128>64", 129, 129, 256, 512, 3, 2, 0), ("skip 128>64", 127, 127, 256, 512, 1, 2, 0),
+         ("conv1 64", 64, 64, 512, 512, 3, 1, 1), ("conv2 64>32", 65, 65, 512, 512, 3, 2, 0),
+         ("skip 64>32", 63, 63, 512, 512, 1, 2, 0), ("conv1 32", 32, 32, 512, 512, 3, 1, 1),
+         ("conv2 32>16", 33, 33, 512, 512, 3, 2, 0), ("skip 32>16", 31, 31, 512, 512, 1, 2, 0),
+         ("conv1 16", 16, 16, 512, 512, 3, 1, 1), ("conv2 16>8", 17, 17, 512, 512, 3, 2, 0),
+         ("skip 16>8", 15, 15, 512, 512, 1, 2, 0), ("conv1 8", 8, 8, 512, 512, 3, 1, 1),
+         ("conv2 8>4", 9, 9, 512, 512, 3, 2, 0), ("skip 8>4", 7, 7, 512, 512, 1, 2, 0), ("final 4", 4, 4, 544, 512, 3, 1, 1)]
+    g = [("conv 4", 4, 4, 512, 512, False)]
+    for r, ci, co in ((4, 512, 512), (8, 512, 512), (16, 512, 512), (32, 512, 512), (64, 512, 256), (128, 256, 128)):
+        g += [(f"up {r}>{2 * r}", r, r, ci, co, True), (f"conv {2 * r}", 2 * r, 2 * r, co, co, False)]
+    out = []
+    for name, h, w, ci, co, k, s_, p_ in d:
+        out.append((f"D b4 {name}", 4, h, w, ci, co, k, s_, p_, False, ("fprop", "dgrad", "wgrad")))      # D step
+        out.append((f"D b2 {name}", 2, h, w, ci, co, k, s_, p_, False, ("fprop", "dgrad")))               # G step
+    for name, h, w, ci, co, tr in g:
+        cfg = (3, 2, 0) if tr else (3, 1, 1)
+        out.append((f"G b2 {name}", 2, h, w, ci, co, *cfg, tr, ("fprop", "fprop", "dgrad", "wgrad")))     # D step + G step
+    return out
+
+
+def conv_step_profile(device, tf32_peak, ms_per_step, with_cudnn=True):
+    """Every convolution launch of one plain adaptation iteration, timed live (CUDA events on the launching stream, L2
+    flushed before each launch) on the tcgen05 kernels and -- the bar SURVEY 2a sets -- on cuDNN's TF32 kernels for the
+    same call.  Aggregates per kernel: algorithmic flops / summed duration."""
+    import math
+    from rick_b200 import conv
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    cl = lambda t: t.contiguous(memory_format=torch.channels_last)
+    agg = {"fprop": [0.0, 0.0, 0.0, 0], "dgrad": [0.0, 0.0, 0.0, 0], "wgrad": [0.0, 0.0, 0.0, 0]}   # flops, us tc, us cudnn, n
+    table = []
+    prev_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        for name, b, h, w, cin, cout, k, stride, pad, tr, prims in _iteration_convs():
+            cfg = (stride, pad, tr)
+            x = cl(torch.randn(b, cin, h, w, device=device))
+            wt = cl(torch.randn(cout, cin, k, k, device=device) / math.sqrt(cin * k * k))
+            y = conv._fprop(x, wt, cfg)
+            g = cl(torch.randn_like(y))
+            flops = 2.0 * b * cin * cout * k * k * (h * w if tr else y.shape[2] * y.shape[3])
+            fns = {"fprop": lambda: conv._fprop(x, wt, cfg), "dgrad": lambda: conv._dgrad(g, wt, x, cfg),
+                   "wgrad": lambda: conv._wgrad(g, x, wt, cfg)}
+            row = {"layer": name, "gflop": round(flops / 1e9, 2)}
+            for prim in dict.fromkeys(prims):
+                conv._FORCE = ""
+                us = _time_kernel(fns[prim], flush, iters=4, warm=2) * 1e3
+                us_lib = None
+                if with_cudnn:
+                    conv._FORCE = "cudnn"
+                    us_lib = _time_kernel(fns[prim], flush, iters=4, warm=2) * 1e3
+                    conv._FORCE = ""
+                n = prims.count(prim)
+                a = agg[prim]
+                a[0] += flops * n
+                a[1] += us * n
+                a[2] += (us_lib or 0.0) * n
+                a[3] += n
+                row[prim] = [round(us, 1), None if us_lib is None else round(us_lib, 1)]
+            table.append(row)
+            del x, wt, y, g
+    finally:
+        conv._FORCE = ""
+        torch.backends.cudnn.allow_tf32 = prev_tf32
+
+    def entry(kernel, prims, note):
+        fl = sum(agg[p][0] for p in prims)
+        us = sum(agg[p][1] for p in prims)
+        us_lib = sum(agg[p][2] for p in prims)
+        ach = fl / (us * 1e-6) / 1e12
+        return {"kernel": kernel, "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
+                "frac": ach / tf32_peak, "traffic": _traffic(kernel),
+                "peak_source": "measured in this run: torch.matmul TF32 8192^3, best of 10 (MEASURED_PEAKS.json has "
+                               "bf16 only: bf16_tflops / 2 = %.1f)" % (load_peaks()["bf16_tflops"] / 2),
+                "launches_per_iteration": sum(agg[p][3] for p in prims), "sum_launch_us": us,
+                "share_of_step": us * 1e-3 / ms_per_step, "algorithmic_flops_per_iteration": fl,
+                "cudnn_tf32_same_launches_us": us_lib if with_cudnn else None, "note": note}
+    total_flops = sum(a[0] for a in agg.values())
+    roof = entry("conv_tc_kernel", ("fprop", "dgrad"),
+                 "all forward + data-gradient convolution launches of one plain iteration (D on the joint batch of 4, "
+                 "G and D on batch 2; includes the split-K fold of the small maps); the per-launch python / ctypes "
+                 "dispatch is inside each timing, so the small maps read low")
+    roof["step"] = {"algorithmic_tflop_per_iteration": total_flops / 1e12,
+                    "achieved_tflops": total_flops / 1e12 / (ms_per_step / 1e3),
+                    "frac": total_flops / 1e12 / (ms_per_step / 1e3) / tf32_peak,
+                    "note": "convolution flops of a PLAIN iteration over the measured ms_per_step (the timed steps also "
+                            "contain R1 / path-length iterations whose extra work is not counted: conservative)"}
+    wg = entry("conv_wgrad_kernel", ("wgrad",), "all weight-gradient launches of one plain iteration, fold kernel included")
+    return {"roofline": roof, "wgrad": wg, "table": table}
 
 
 @torch.no_grad()
-def g_samples_per_s(G, device, batches=6, batch=64, fused=False):
+def g_samples_per_s(G, device, batches=6, batch=64, fused=False, library=False):
+    """``library=True``: the module path with its convolutions forced onto the library (cuDNN) for comparison."""
+    from rick_b200 import conv
     from rick_b200.adapt import generate_samples
     G.eval()
+    conv._FORCE = "cudnn" if library else ""
     it = generate_samples(G, (batches + 2) * batch, batch, seed=1000, fused=fused)
     next(it), next(it)
     torch.cuda.synchronize()
@@ -458,6 +597,7 @@ def g_samples_per_s(G, device, batches=6, batch=64, fused=False):
         n += img.shape[0]
     e.record()
     e.synchronize()
+    conv._FORCE = ""
     return n / (s.elapsed_time(e) / 1e3)
 
 
