@@ -334,19 +334,34 @@ def _flush_l2(buf):
     buf.zero_()          # 256 MB write > 126 MB L2
 
 
-def _time_kernel(fn, flush_buf, iters=10, warm=3):
-    """average device time of fn() in ms: CUDA events on the launching stream, L2 flushed before every launch."""
+def _time_kernel(fn, flush_buf, iters=10, warm=3, graph=True):
+    """average device time of fn() in ms: CUDA events on the launching stream, L2 flushed before every launch.  The call
+    is replayed from a CUDA graph (as the timed iteration replays it), so the Python / ctypes / autograd dispatch of
+    ``fn`` -- 20-50 us, more than a small-map kernel takes -- is not inside the events; eager launch when a call cannot
+    be captured."""
     for _ in range(warm):
         fn()
+    g = None
+    if graph:
+        torch.cuda.synchronize()
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                keep = fn()                        # noqa: F841  (outputs live in the graph's pool until g is dropped)
+            g.replay()
+        except Exception:
+            g = None
+            torch.cuda.synchronize()
     times = []
     for _ in range(iters):
         _flush_l2(flush_buf)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        fn()
+        g.replay() if g is not None else fn()
         e.record()
         e.synchronize()
         times.append(s.elapsed_time(e))
+    del g
     return sum(times) / len(times)
 
 
@@ -569,8 +584,8 @@ def conv_step_profile(device, tf32_peak, ms_per_step, with_cudnn=True):
     total_flops = sum(a[0] for a in agg.values())
     roof = entry("conv_tc_kernel", ("fprop", "dgrad"),
                  "all forward + data-gradient convolution launches of one plain iteration (D on the joint batch of 4, "
-                 "G and D on batch 2; includes the split-K fold of the small maps); the per-launch python / ctypes "
-                 "dispatch is inside each timing, so the small maps read low")
+                 "G and D on batch 2; includes the split-K fold of the small maps); each launch replayed from a CUDA "
+                 "graph between the events, as the timed iteration replays it")
     roof["step"] = {"algorithmic_tflop_per_iteration": total_flops / 1e12,
                     "achieved_tflops": total_flops / 1e12 / (ms_per_step / 1e3),
                     "frac": total_flops / 1e12 / (ms_per_step / 1e3) / tf32_peak,

@@ -157,10 +157,16 @@ class RickAdapter:
         self.g_train = [p for n, p in self.g_named.items() if "convs" in n]
         self.d_train = [p for n, p in self.d_named.items()
                         if ("convs" in n and "convs.0" not in n) or "final" in n]
+        # DDP exchange step (world_size > 1).  The generator's modulation layers hang off one autograd node (their
+        # gradients land together when backward ends): last bucket.  D's equalised-lr scaling runs as one node per
+        # bucket, so that a bucket's gradients reach the leaves -- and its all-reduce starts -- while backward goes on.
+        g_late = [p for n, p in self.g_named.items() if "convs" in n and "modulation" in n]
+        self._gsync = {"g": rdist.GradSync(self.g_train, late=g_late), "d": rdist.GradSync(self.d_train)}
         if self.device.type == "cuda":
             from . import stylegan2 as _sg
             _sg.declare_prescale_groups(generator, self.g_train)          # trainable subset | rest
-            _sg.declare_prescale_groups(discriminator, self.d_train)
+            _sg.declare_prescale_groups(discriminator, *(self._gsync["d"].buckets if rdist.world_size() > 1
+                                                         else [self.d_train]))
             _sg.declare_prescale_groups(g_ema, list(g_ema.parameters()))    # the Fisher round differentiates all of them
             _sg.declare_prescale_groups(d_ema, list(d_ema.parameters()))
         self.acc_g = rick.FisherAccumulator(g_ema.named_parameters())
@@ -281,8 +287,7 @@ class RickAdapter:
         self.d.zero_grad(set_to_none=True)
         # only the trainable subset needs gradients (train:921-931 hands exactly these to the optimiser); asking for
         # them alone skips the from-RGB weight gradient and everything upstream of it
-        autograd.backward(d_loss, inputs=[p for p in self.d_train if p.requires_grad])
-        self._sync_grads(self.d_train)
+        self._backward("d", d_loss, [p for p in self.d_train if p.requires_grad])
         r1_iter = i % cfg.d_reg_every == 0
         path_iter = i % cfg.g_reg_every == 0 and after_warmup
         # with the fused optimiser the EMA rides on the LAST update of each network in this iteration (the weights do
@@ -296,9 +301,8 @@ class RickAdapter:
             real_pred = real_pred.view(real_r.size(0), -1).mean(dim=1).unsqueeze(1)
             r1_loss = d_r1_loss(real_pred, real_r)
             self.d.zero_grad(set_to_none=True)
-            autograd.backward(cfg.r1 / 2 * r1_loss * cfg.d_reg_every + 0 * real_pred[0],
-                              inputs=[p for p in self.d_train if p.requires_grad])
-            self._sync_grads(self.d_train)
+            self._backward("d", cfg.r1 / 2 * r1_loss * cfg.d_reg_every + 0 * real_pred[0],
+                           [p for p in self.d_train if p.requires_grad])
             self._optim_step("d", after_warmup, ema=True)
             out["r1"] = r1_loss.detach()
 
@@ -311,8 +315,7 @@ class RickAdapter:
             fake_pred, _ = self.d(fake_img)
             g_loss = g_nonsaturating_loss(fake_pred)
             self.g.zero_grad(set_to_none=True)
-            autograd.backward(g_loss, inputs=self.g_train)
-            self._sync_grads(self.g_train)
+            self._backward("g", g_loss)
             self._optim_step("g", True, ema=not path_iter)
         else:
             with torch.no_grad():                       # warm-up: the loss is only logged (train:518-519)
@@ -333,8 +336,7 @@ class RickAdapter:
             weighted = cfg.path_regularize * cfg.g_reg_every * path_loss
             if cfg.path_batch_shrink:
                 weighted = weighted + 0 * fake_img[0, 0, 0, 0]
-            autograd.backward(weighted, inputs=self.g_train)
-            self._sync_grads(self.g_train)
+            self._backward("g", weighted)
             self._optim_step("g", True, ema=True)
             out["path"], out["path_length"] = path_loss.detach(), path_lengths.mean().detach()
 
@@ -356,11 +358,14 @@ class RickAdapter:
                                                                  force=force_masks)
         opt.step()
 
-    @staticmethod
-    def _sync_grads(params):
-        """DDP exchange step: average the gradients over ranks (no-op in a single process)."""
-        if rdist.world_size() > 1:
-            rdist.allreduce_mean_([p.grad for p in params if p.grad is not None])
+    def _backward(self, net: str, loss: torch.Tensor, inputs=None):
+        """Backward pass of network ``net`` ("g" / "d") into its trainable parameters, with the DDP exchange step
+        (average of the gradients over ranks; nothing in a single process) overlapped: rick_b200.dist.GradSync launches
+        each bucket's all-reduce as soon as backward has produced it and the call returns once all have landed."""
+        sync = self._gsync[net]
+        sync.begin()
+        autograd.backward(loss, inputs=(self.g_train if net == "g" else self.d_train) if inputs is None else inputs)
+        sync.finish()
 
     @torch.no_grad()
     def _ema(self):

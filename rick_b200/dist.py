@@ -5,9 +5,13 @@ CPU tests).  Only the exchange steps the path really has:
                         statistics (sum x, sum x x^T, count; float64) when an Inception-style statistic is requested
                         -- the reference gathers nothing because it is single-process (gan_training/eval.py:31-46,
                         metrics/fid_score.py:132-142 computes mean / cov on one host).
-  * adaptation          DDP-style gradient averaging: flat fp32 buckets all-reduced (SUM) and scaled by 1/world, issued
-                        as soon as backward finishes (the reference's nn.DataParallel re-broadcasts ~235 MB of
-                        parameters on every forward instead, train:941-944).
+  * adaptation          DDP-style gradient averaging, overlapped with the backward pass (``GradSync``): the trainable
+                        parameters are cut into a few buckets in the order backward produces them; the moment a
+                        bucket's last gradient lands, ONE grouped NCCL all-reduce (AVG, in place on the gradient
+                        tensors -- no flat copy, no scaling pass) is issued asynchronously on the process group's own
+                        stream while backward continues on the compute stream; the optimiser step waits for the
+                        handles.  Recorded inside the CUDA graphs as a fork / join.  (The reference's
+                        nn.DataParallel re-broadcasts ~235 MB of parameters on every forward instead, train:941-944.)
   * Fisher round        images sharded over ranks, one all-reduce (SUM) of the grad^2 accumulators; every rank then
                         derives identical masks from identical Fisher tensors (no further traffic).
 """
@@ -113,6 +117,105 @@ def _allreduce_buckets_(tensors: Sequence[torch.Tensor], scale: float, bucket_by
         if size >= bucket_bytes:
             flush()
     flush()
+
+
+class GradSync:
+    """The DDP exchange step of one network, overlapped with its backward pass.
+
+    ``params`` are the trainable parameters in registration (= forward) order; backward produces their gradients
+    roughly in reverse, so bucket 0 holds the LAST layers; buckets are exchanged in index order.  Usage per pass::
+
+        sync.begin()                       # arm the hooks
+        autograd.backward(loss, inputs=params)
+        sync.finish()                      # launch whatever has not fired, wait for every handle
+
+    A bucket is launched from the post-accumulate-grad hook of the parameter that completes it: one coalesced
+    all-reduce over the bucket's gradient tensors where they lie (``ncclGroupStart/End`` around one all-reduce per
+    tensor: a single NCCL kernel), ``async_op=True`` so that it runs on the process group's communication stream behind
+    an event dependency on the compute stream.  NCCL averages natively (``ReduceOp.AVG``); gloo (CPU tests) sums and the
+    1 / world multiply happens in ``finish``.  Every rank runs the same program, so hooks fire in the same order
+    everywhere; gradients a pass does not produce (restricted backward) are simply absent from their bucket on all
+    ranks alike."""
+
+    def __init__(self, params: Sequence[torch.Tensor], n_buckets: int = 4, late: Sequence[torch.Tensor] = ()):
+        """``late``: parameters whose gradients only land when the whole backward pass is over (they hang off one
+        multi-output autograd node, e.g. all modulation layers of the generator): kept out of the early buckets so
+        that those can complete -- and start their exchange -- while backward is still running."""
+        self.params = list(params)
+        self.world = world_size()
+        late_ids = {id(p) for p in late}
+        rev = [p for p in reversed(self.params) if id(p) not in late_ids]
+        tail = [p for p in self.params if id(p) in late_ids]
+        total = sum(p.numel() for p in rev)
+        self.buckets: List[List[torch.Tensor]] = [[]]
+        acc = 0
+        for p in rev:
+            if self.buckets[-1] and len(self.buckets) < n_buckets and acc >= total * len(self.buckets) / n_buckets:
+                self.buckets.append([])
+            self.buckets[-1].append(p)
+            acc += p.numel()
+        if tail:
+            self.buckets.append(tail)
+        self.buckets = [b for b in self.buckets if b]
+        self._bucket_of = {id(p): k for k, b in enumerate(self.buckets) for p in b}
+        self._pending = [0] * len(self.buckets)
+        self._launched = [True] * len(self.buckets)
+        self._next = 0
+        self._works: list = []
+        self._armed = False
+        self._avg = None
+        self._handles = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params] if self.world > 1 else []
+
+    def begin(self):
+        if self.world == 1:
+            return
+        self._pending = [len(b) for b in self.buckets]
+        self._launched = [False] * len(self.buckets)
+        self._next = 0
+        self._works = []
+        self._armed = True
+
+    def _hook(self, p):
+        if not self._armed:
+            return
+        self._pending[self._bucket_of[id(p)]] -= 1
+        # buckets are launched strictly in index order, so the sequence of collectives is the same on every rank
+        # whatever order the gradients arrive in
+        while self._next < len(self.buckets) and self._pending[self._next] == 0:
+            self._launch(self._next)
+            self._next += 1
+
+    def _launch(self, k: int):
+        self._launched[k] = True
+        grads = [p.grad for p in self.buckets[k] if p.grad is not None]
+        if not grads:
+            return
+        if self._avg is None:
+            self._avg = dist.get_backend() == "nccl"
+        op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+        from torch.distributed.distributed_c10d import _coalescing_manager
+        with _coalescing_manager(async_ops=True) as cm:
+            for g in grads:
+                dist.all_reduce(g, op=op)
+        self._works.append((cm, grads))
+
+    def finish(self):
+        if self.world == 1:
+            return
+        self._armed = False
+        for k in range(len(self.buckets)):
+            if not self._launched[k]:
+                self._launch(k)
+        for cm, grads in self._works:
+            cm.wait()
+            if not self._avg:
+                torch._foreach_mul_(grads, 1.0 / self.world)
+        self._works = []
+
+    def remove(self):
+        for h in self._handles:
+            h.remove()
+        self._handles = []
 
 
 def allreduce_mean_(tensors: Sequence[torch.Tensor], bucket_bytes: int = 64 << 20):

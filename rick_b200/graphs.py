@@ -107,8 +107,7 @@ class GraphedRickAdapter(RickAdapter):
         fake_pred, real_pred = d_pair(self.d, fake_img, self._real)
         d_loss = d_logistic_loss(real_pred, fake_pred)
         self.d.zero_grad(set_to_none=True)
-        autograd.backward(d_loss, inputs=self.d_train)
-        self._sync_grads(self.d_train)
+        self._backward("d", d_loss)
         self._optim_step("d", True, force_masks=True)
         return {"d": d_loss.detach(), "real_score": real_pred.mean().detach(), "fake_score": fake_pred.mean().detach()}
 
@@ -120,8 +119,7 @@ class GraphedRickAdapter(RickAdapter):
         real_pred = real_pred.view(real_r.size(0), -1).mean(dim=1).unsqueeze(1)
         r1_loss = d_r1_loss(real_pred, real_r)
         self.d.zero_grad(set_to_none=True)
-        autograd.backward(cfg.r1 / 2 * r1_loss * cfg.d_reg_every + 0 * real_pred[0], inputs=self.d_train)
-        self._sync_grads(self.d_train)
+        self._backward("d", cfg.r1 / 2 * r1_loss * cfg.d_reg_every + 0 * real_pred[0])
         self._optim_step("d", True, force_masks=True)
         return {"r1": r1_loss.detach()}
 
@@ -133,8 +131,7 @@ class GraphedRickAdapter(RickAdapter):
         fake_pred, _ = self.d(fake_img)
         g_loss = g_nonsaturating_loss(fake_pred)
         self.g.zero_grad(set_to_none=True)
-        autograd.backward(g_loss, inputs=self.g_train)
-        self._sync_grads(self.g_train)
+        self._backward("g", g_loss)
         self._optim_step("g", True, force_masks=True)
         return {"g": g_loss.detach()}
 
@@ -150,8 +147,7 @@ class GraphedRickAdapter(RickAdapter):
         weighted = cfg.path_regularize * cfg.g_reg_every * path_loss
         if cfg.path_batch_shrink:
             weighted = weighted + 0 * fake_img[0, 0, 0, 0]
-        autograd.backward(weighted, inputs=self.g_train)
-        self._sync_grads(self.g_train)
+        self._backward("g", weighted)
         self._optim_step("g", True, force_masks=True)
         self.mean_path_length.copy_(path_mean)
         return {"path": path_loss.detach(), "path_length": path_lengths.mean().detach()}

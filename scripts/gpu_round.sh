@@ -8,7 +8,7 @@ echo "cores: $(nproc)" >> gpurun_out/gpu.txt
 for STEP in "$@"; do
 case $STEP in
 tests)
-  for f in ${TEST_FILES:-tests/test_ops_gpu.py tests/test_rick_gpu.py tests/test_conv_tc_gpu.py tests/test_conv_train_gpu.py tests/test_model_gpu.py tests/test_adapt_gpu.py}; do
+  for f in ${TEST_FILES:-tests/test_ops_gpu.py tests/test_rick_gpu.py tests/test_conv_tc_gpu.py tests/test_conv_train_gpu.py tests/test_model_gpu.py tests/test_adapt_gpu.py tests/test_ref_cuda_gpu.py}; do
     log=gpurun_out/pytest_$(basename $f .py).log
     timeout ${TEST_TIMEOUT:-420} python -u -m pytest $f -m gpu -q -rA --timeout=300 -p no:cacheprovider ${PYTEST_ARGS} > $log 2>&1
     echo "=== $f rc=$? : $(tail -1 $log)"
@@ -29,7 +29,11 @@ ncuops)
   timeout 300 ncu --set full --clock-control none --import-source on \
       -k regex:${NCU_KERNELS:-'upfirdn2d|bias_act_vec|bias_act_bwd|blur_nhwc|conv_tc|conv_wgrad|adam_mask_ema'} -s ${NCU_SKIP:-9} -c ${NCU_COUNT:-9} \
       -o gpurun_out/prof_ops${NCU_TAG} python -u ${NCU_SCRIPT:-scripts/prof_ops.py} > gpurun_out/ncu_ops${NCU_TAG}.log 2>&1
-  echo "ncu ops rc=$?" ;;
+  echo "ncu ops rc=$?"
+  # the raw metric page as CSV (small); the report itself only travels back when it fits the 64 MiB pull limit
+  ncu -i gpurun_out/prof_ops${NCU_TAG}.ncu-rep --page raw --csv > gpurun_out/prof_ops${NCU_TAG}_raw.csv 2>/dev/null
+  if [ -n "${NCU_DROP_REP}" ] || [ $(stat -c %s gpurun_out/prof_ops${NCU_TAG}.ncu-rep 2>/dev/null || echo 0) -gt 40000000 ]; then
+    rm -f gpurun_out/prof_ops${NCU_TAG}.ncu-rep; fi ;;
 esac
 done
 ls -la gpurun_out

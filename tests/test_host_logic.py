@@ -124,7 +124,25 @@ def _gloo_worker(rank, world, port, out_dir):
     rd.allreduce_mean_(grads, bucket_bytes=32)
     acc = [torch.full((4,), float(rank + 1))]
     rd.allreduce_sum_(acc)
-    torch.save({"mu": mu, "cov": cov, "grads": grads, "acc": acc}, os.path.join(out_dir, f"r{rank}.pt"))
+    # adaptation, overlapped form: GradSync launches bucket all-reduces from gradient hooks during backward
+    torch.manual_seed(3)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.Tanh(), torch.nn.Linear(16, 16), torch.nn.Tanh(),
+                              torch.nn.Linear(16, 4))
+    params = list(net.parameters())
+    sync = rd.GradSync(params, n_buckets=3, late=[params[1]])
+    assert sum(len(b) for b in sync.buckets) == len(params) and sync.buckets[-1] == [params[1]]
+    synced = []
+    for step in range(2):                                   # second pass: counters re-armed, one gradient absent
+        xin = torch.randn(5, 6, generator=torch.Generator().manual_seed(100 * step + rank))
+        net.zero_grad(set_to_none=True)
+        inputs = params if step == 0 else params[:-1]
+        lg = torch.autograd.grad(net(xin).pow(2).sum(), inputs)       # this rank's own gradients (no hooks fire)
+        local = [lg[k].clone() if k < len(inputs) else None for k in range(len(params))]
+        sync.begin()
+        torch.autograd.backward(net(xin).pow(2).sum(), inputs=inputs)
+        sync.finish()
+        synced.append(([None if p.grad is None else p.grad.clone() for p in params], local))
+    torch.save({"mu": mu, "cov": cov, "grads": grads, "acc": acc, "synced": synced}, os.path.join(out_dir, f"r{rank}.pt"))
     rd.barrier()
     dist.destroy_process_group()
 
@@ -140,6 +158,17 @@ def test_world_size_2_gloo_exchange_steps(tmp_path):
         np.testing.assert_allclose(o["cov"].numpy(), np.cov(feats, rowvar=False), rtol=1e-10, atol=1e-12)
         assert torch.equal(o["grads"][0], torch.full((3, 5), 1.5)) and torch.equal(o["grads"][1], torch.full((7,), 15.0))
         assert torch.equal(o["acc"][0], torch.full((4,), 3.0))
+    outs = [torch.load(os.path.join(tmp_path, f"r{r}.pt")) for r in range(world)]
+    for step in range(2):
+        locals_ = [o["synced"][step][1] for o in outs]
+        for r in range(world):
+            got = outs[r]["synced"][step][0]
+            for k, g in enumerate(got):
+                if g is None:
+                    assert step == 1 and all(l[k] is None for l in locals_)
+                    continue
+                want = sum(l[k] for l in locals_) / world
+                torch.testing.assert_close(g, want, rtol=1e-6, atol=1e-7)
 
 
 def _emulate_conv_geom(x_nhwc, wt, g):
