@@ -152,6 +152,48 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const in
     }
 }
 
+// Stage B for tiles of ONE sample (every large feature map): the accumulator arrives with lane = output channel and
+// column = pixel, which stored directly is one 4-byte store instruction per pixel and lane plus its 64-bit address
+// arithmetic and a branch -- ~15 issue slots per column on a warp that has its scheduler to itself (IPC 0.13 in the
+// round-2 source-level profile: 14.7 us per 128 x 256 tile, as long as the whole main loop of a Cin = 128 layer, so
+// every short-K launch was bound by its epilogue).  Here the warp applies the epilogue with lane = channel, transposes
+// its 32 x 32 block through shared memory (conflict-free both ways) and stores with 8 lanes per pixel: 8 predicated
+// 128-bit stores per 32 columns instead of 32 branchy 32-bit ones.
+template <bool ACT, bool DUAL>
+__device__ __forceinline__ void epilogue_chunk_t(const uint32_t (&v)[32], const int* __restrict__ offtab,
+                                                 const float* __restrict__ nztab, float* __restrict__ stage,
+                                                 float* __restrict__ outq, long long out2_delta, int lane, bool grp_ok,
+                                                 float bias, float alpha, float scale, float dm, float sn,
+                                                 const float4 sn4) {
+#pragma unroll
+    for (int j4 = 0; j4 < 32; j4 += 4) {
+        const float4 nq = *reinterpret_cast<const float4*>(nztab + j4);
+        const float nzs[4] = {nq.x, nq.y, nq.z, nq.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float r = fmaf(__uint_as_float(v[j4 + k]), dm, nzs[k]) + bias;
+            if (ACT) r = (r > 0.f ? r : r * alpha) * scale;
+            if (!DUAL) r *= sn;                            // sn == 1 unless only the modulated copy is wanted
+            stage[(j4 + k) * 32 + lane] = r;
+        }
+    }
+    __syncwarp();
+    const int sub = lane >> 3, c4 = (lane & 7) * 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int j = i * 4 + sub;
+        const int off = offtab[j];
+        const float4 val = *reinterpret_cast<const float4*>(stage + j * 32 + c4);
+        if (off >= 0 && grp_ok) {
+            float* dst = outq + off + c4;
+            *reinterpret_cast<float4*>(dst) = val;
+            if (DUAL)
+                *reinterpret_cast<float4*>(dst + out2_delta) = make_float4(val.x * sn4.x, val.y * sn4.y, val.z * sn4.z, val.w * sn4.w);
+        }
+    }
+    __syncwarp();                                          // the block is re-used by the next chunk
+}
+
 template <bool ACT, bool DUAL>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x0,
@@ -170,6 +212,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     __shared__ __align__(16) int ep_pix[2 * kMaxN];      // element offset of (pixel, channel 0) or -1
     __shared__ __align__(16) float ep_nz[2 * kMaxN];     // noise_w * noise
     __shared__ short ep_b[2 * kMaxN];                    // sample index
+    __shared__ __align__(16) float ep_stage[4 * 32 * 32];  // per epilogue warp: one 32 pixel x 32 channel block in transit
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -200,6 +243,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         // ===================================================== TMA producer
         if (lane == 0) {
             uint32_t it = 0;
+            const uint32_t smem_base = tc::smem_u32(smem);
+            const uint32_t full_base = tc::smem_u32(full_bar), empty_base = tc::smem_u32(empty_bar);
             for (int vt = blockIdx.x; vt < p.total_tiles * p.ksplit; vt += gridDim.x) {
                 const int t = vt / p.ksplit, sp = vt - t * p.ksplit;
                 const TileCoord c = decode_tile(p, t);
@@ -224,66 +269,71 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                 const int n_k = P.n_taps * p.kblocks;
                 const int k0 = n_k * sp / p.ksplit, k1 = n_k * (sp + 1) / p.ksplit;
                 int tap = k0 / p.kblocks, kb = k0 - tap * p.kblocks;
-                for (int kk = k0; kk < k1; ++kk, ++it) {
-                    const int gx = c.x0 * p.in_stride + P.dx[tap];
-                    const int gy = c.y0 * p.in_stride + P.dy[tap];
-                    const int s = it % kStages;
-                    tc::mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
-                    uint8_t* a_dst = smem + s * stage_bytes;
-                    uint8_t* b_dst = a_dst + kABytes;
-                    tc::mbar_arrive_expect_tx(&full_bar[s], kABytes + P.box_bytes);
-                    if (!p.a_mn) {
-                        tc::tma_load_3d(a_dst, &tmap_w, &full_bar[s], kb * kBlockK, c.cout0, P.widx[tap]);
-                    } else {            // MN-major: four blocks of 32 M-channels x 32 K-rows (4 KB each), one 4-D box
-                        tc::tma_load_4d(a_dst, &tmap_w, &full_bar[s], 0, kb * kBlockK, P.widx[tap], c.cout0 / 32);
+                // Per stage this thread only waits, posts the byte count and issues two TMAs: everything that depends on
+                // the tile or the tap is hoisted (the flat loop it replaces re-derived tap offsets, tensor map and
+                // shared addresses every stage: ~100 dependent instructions = 0.27 us of the 0.41 us a stage lasts,
+                // straight out of the latency budget of a 4-stage ring -- round-2 source-level profile).
+                const int bx = c.x0 * p.in_stride, by = c.y0 * p.in_stride;
+                const uint32_t tx_bytes = kABytes + P.box_bytes;
+                const int a_mn = p.a_mn, kblocks = p.kblocks, cb = c.b0, cm = a_mn ? c.cout0 / 32 : c.cout0;
+                for (int kk = k0; kk < k1; ++tap, kb = 0) {
+                    const int gx = bx + P.dx[tap], gy = by + P.dy[tap], wi = P.widx[tap];
+                    int kb_end = kb + (k1 - kk);
+                    if (kb_end > kblocks) kb_end = kblocks;
+                    for (; kb < kb_end; ++kb, ++kk, ++it) {
+                        const uint32_t s = it % kStages;
+                        const uint32_t a_dst = smem_base + s * stage_bytes;
+                        const uint32_t full = full_base + s * 8;
+                        tc::mbar_wait_u32(empty_base + s * 8, ((it / kStages) & 1) ^ 1);
+                        tc::mbar_arrive_expect_tx_u32(full, tx_bytes);
+                        if (!a_mn)
+                            tc::tma_load_3d_u32(a_dst, &tmap_w, full, kb * kBlockK, cm, wi);
+                        else            // MN-major: four blocks of 32 M-channels x 32 K-rows (4 KB each), one 4-D box
+                            tc::tma_load_4d_u32(a_dst, &tmap_w, full, 0, kb * kBlockK, wi, cm);
+                        tc::tma_load_4d_u32(a_dst + kABytes, tmap_x, full, kb * kBlockK, gx, gy, cb);
                     }
-                    tc::tma_load_4d(b_dst, tmap_x, &full_bar[s], kb * kBlockK, gx, gy, c.b0);
-                    if (++kb == p.kblocks) kb = 0, ++tap;
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================================================== MMA issuer
-        uint32_t it = 0;
-        uint32_t tile_n = 0;
-        for (int vt = blockIdx.x; vt < p.total_tiles * p.ksplit; vt += gridDim.x, ++tile_n) {
-            const int t = vt / p.ksplit, sp = vt - t * p.ksplit;
-            const TileCoord c = decode_tile(p, t);
-            const int n_k = p.phase[c.phase].n_taps * p.kblocks;
-            const int n_kblocks = n_k * (sp + 1) / p.ksplit - n_k * sp / p.ksplit;       // iterations of this range (>= 1)
-            const uint32_t idesc = tc::umma_idesc_tf32(kBlockM, p.phase[c.phase].n_mma, p.a_mn != 0, false);
-            const uint32_t acc = tile_n & 1;
-            tc::mbar_wait(&tmem_empty[acc], ((tile_n >> 1) & 1) ^ 1);
-            tc::tc_fence_after_sync();
-            const uint32_t d_tmem = tmem_base + acc * kMaxN;
-            for (int kb = 0; kb < n_kblocks; ++kb, ++it) {
-                const int s = it % kStages;
-                tc::mbar_wait(&full_bar[s], (it / kStages) & 1);
+        // ===================================================== MMA issuer (one thread; descriptors are slot-affine)
+        if (lane == 0) {
+            uint32_t it = 0;
+            uint32_t tile_n = 0;
+            const uint32_t smem_base = tc::smem_u32(smem);
+            const uint32_t full_base = tc::smem_u32(full_bar), empty_base = tc::smem_u32(empty_bar);
+            const uint32_t tfull_base = tc::smem_u32(tmem_full), tempty_base = tc::smem_u32(tmem_empty);
+            // stage slot s lives stage_bytes further on: its descriptors are those of slot 0 plus s * (stage_bytes >> 4)
+            // in the 14-bit start-address field (all of shared memory fits, so no carry into the next field)
+            const uint64_t a_desc0 = p.a_mn ? tc::umma_desc_mn_sw128_32b(smem_base, kBlockK * 128)
+                                            : tc::umma_desc_k_sw128(smem_base);
+            const uint64_t b_desc0 = tc::umma_desc_k_sw128(smem_base + kABytes);
+            const uint32_t a_kstep = p.a_mn ? (1024u >> 4) : 2u;    // 8 tf32 along K: 8 rows of 128 B (MN-major) / 32 B
+            for (int vt = blockIdx.x; vt < p.total_tiles * p.ksplit; vt += gridDim.x, ++tile_n) {
+                const int t = vt / p.ksplit, sp = vt - t * p.ksplit;
+                const TileCoord c = decode_tile(p, t);
+                const int n_k = p.phase[c.phase].n_taps * p.kblocks;
+                const int n_kblocks = n_k * (sp + 1) / p.ksplit - n_k * sp / p.ksplit;   // iterations of this range (>= 1)
+                const uint32_t idesc = tc::umma_idesc_tf32(kBlockM, p.phase[c.phase].n_mma, p.a_mn != 0, false);
+                const uint32_t acc = tile_n & 1;
+                tc::mbar_wait_u32(tempty_base + acc * 8, ((tile_n >> 1) & 1) ^ 1);
                 tc::tc_fence_after_sync();
-                if (tc::elect_one()) {
-                    const uint32_t a_addr = tc::smem_u32(smem + s * stage_bytes);
-                    const uint64_t b_desc = tc::umma_desc_k_sw128(a_addr + kABytes);
-                    if (!p.a_mn) {
-                        const uint64_t a_desc = tc::umma_desc_k_sw128(a_addr);
+                const uint32_t d_tmem = tmem_base + acc * kMaxN;
+                for (int kb = 0; kb < n_kblocks; ++kb, ++it) {
+                    const uint32_t s = it % kStages;
+                    tc::mbar_wait_u32(full_base + s * 8, (it / kStages) & 1);
+                    tc::tc_fence_after_sync();
+                    const uint64_t a_desc = a_desc0 + (uint64_t)(s * (uint32_t)(stage_bytes >> 4));
+                    const uint64_t b_desc = b_desc0 + (uint64_t)(s * (uint32_t)(stage_bytes >> 4));
 #pragma unroll
-                        for (int k = 0; k < kBlockK / 8; ++k) {
-                            // advance 8 tf32 = 32 bytes along K inside the swizzled row: +2 in the (addr >> 4) field
-                            tc::umma_tf32_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-                        }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < kBlockK / 8; ++k) {
-                            // MN-major A: 8 K-rows = 1024 B further down each 32-channel block
-                            const uint64_t a_desc = tc::umma_desc_mn_sw128_32b(a_addr + k * 1024, kBlockK * 128);
-                            tc::umma_tf32_ss(d_tmem, a_desc, b_desc + 2 * k, idesc, (kb | k) != 0);
-                        }
-                    }
-                    tc::umma_commit(&empty_bar[s]);                       // smem stage reusable once these MMAs retire
-                    if (kb == n_kblocks - 1) tc::umma_commit(&tmem_full[acc]);   // accumulator complete
+                    for (int k = 0; k < kBlockK / 8; ++k)
+                        tc::umma_tf32_ss(d_tmem, a_desc + (uint64_t)(k * a_kstep), b_desc + 2 * k, idesc, (kb | k) != 0);
+                    tc::umma_commit_u32(empty_base + s * 8);               // smem stage reusable once these MMAs retire
+                    if (kb == n_kblocks - 1) tc::umma_commit_u32(tfull_base + acc * 8);   // accumulator complete
                 }
-                __syncwarp();
             }
         }
+        __syncwarp();
     } else {
         // ===================================================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
         // Per tile, stage A (overlaps the MMAs of this tile): the 128 epilogue threads decode the tile's <= 256 columns
@@ -332,22 +382,59 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             tc::mbar_wait(&tmem_full[acc], (tile_n >> 1) & 1);
             tc::tc_fence_after_sync();
             const uint32_t taddr = tmem_base + acc * kMaxN + (static_cast<uint32_t>(quarter * 32) << 16);
-            float* const outp = p.out + co + (long long)sp * p.split_plane;
             const long long out2_delta = DUAL ? (p.out2 - p.out) : 0;
-            for (int n0 = 0; n0 < n_valid; n0 += 32) {
-                uint32_t v[32];
-                tc::tmem_ld_32x32b_x32(taddr + n0, v);
-                tc::tmem_ld_wait();
-                if (P.nb > 1)
+            if (P.nb > 1) {                 // several samples per tile (small maps): per-column sample switch, direct stores
+                float* const outp = p.out + co + (long long)sp * p.split_plane;
+                for (int n0 = 0; n0 < n_valid; n0 += 32) {
+                    uint32_t v[32];
+                    tc::tmem_ld_32x32b_x32(taddr + n0, v);
+                    tc::tmem_ld_wait();
                     epilogue_chunk<ACT, DUAL, true>(v, pixtab + n0, nztab + n0, btab + n0, outp, out2_delta, p, co, co_ok,
                                                     bias, alpha, scale, dm, sn, cur_b);
-                else
-                    epilogue_chunk<ACT, DUAL, false>(v, pixtab + n0, nztab + n0, btab + n0, outp, out2_delta, p, co, co_ok,
-                                                     bias, alpha, scale, dm, sn, cur_b);
+                }
+                tc::tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
+            } else {
+                // one sample per tile: transposed 128-bit stores; the TMEM loads run one chunk ahead of the stores and the
+                // accumulator is handed back to the MMA warp as soon as its last chunk sits in registers
+                const int c4 = (lane & 7) * 4;
+                const bool grp_ok = c.cout0 + quarter * 32 + c4 < p.cout;
+                float* const outq = p.out + c.cout0 + quarter * 32 + (long long)sp * p.split_plane;
+                float4 sn4 = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (DUAL && grp_ok) {
+                    const float* sp4 = p.s_next + (size_t)cur_b * p.cout + c.cout0 + quarter * 32 + c4;
+                    sn4 = make_float4(__ldg(sp4), __ldg(sp4 + 1), __ldg(sp4 + 2), __ldg(sp4 + 3));
+                }
+                float* const stage = ep_stage + quarter * 1024;
+                uint32_t va[32], vb[32];
+                tc::tmem_ld_32x32b_x32(taddr, va);
+                for (int n0 = 0; n0 < n_valid; n0 += 64) {
+                    const bool more1 = n0 + 32 < n_valid, more2 = n0 + 64 < n_valid;
+                    tc::tmem_ld_wait();
+                    if (more1) {
+                        tc::tmem_ld_32x32b_x32(taddr + n0 + 32, vb);
+                    } else {
+                        tc::tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
+                    }
+                    epilogue_chunk_t<ACT, DUAL>(va, pixtab + n0, nztab + n0, stage, outq, out2_delta, lane, grp_ok, bias,
+                                                alpha, scale, dm, sn, sn4);
+                    if (more1) {
+                        tc::tmem_ld_wait();
+                        if (more2) {
+                            tc::tmem_ld_32x32b_x32(taddr + n0 + 64, va);
+                        } else {
+                            tc::tc_fence_before_sync();
+                            __syncwarp();
+                            if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
+                        }
+                        epilogue_chunk_t<ACT, DUAL>(vb, pixtab + n0 + 32, nztab + n0 + 32, stage, outq, out2_delta, lane,
+                                                    grp_ok, bias, alpha, scale, dm, sn, sn4);
+                    }
+                }
             }
-            tc::tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
         }
     }
 
@@ -635,30 +722,40 @@ int plan_tiles(const rick_conv_geom* g, TilePlan& tp) {
         if (g->phase[i].n_taps < 1 || g->phase[i].n_taps > 9) return RICK_ERR_INVALID_ARGUMENT;
         if (g->phase[i].rows < 1 || g->phase[i].cols < 1) return RICK_ERR_INVALID_ARGUMENT;
     }
+    // Single-phase launches are also costed by WAVES over the SMs: 512 tiles of 256 pixels on 148 SMs run as 4 rounds
+    // of which the last is half empty, 592 tiles of 224 pixels (32 x 7) as 4 full, shorter ones (the batch-2 layers of
+    // the G step: 1/8 less time).  Several tile heights are tried per width for that reason.
+    const long long outer = ceil_div(g->cout, kBlockM);
+    const bool by_waves = g->n_phases == 1;
     auto choose_tile = [&](int rows, int cols, int& tw, int& th, int& nb) {
         double best = -1.0;
         const int max_side = 256 / g->in_stride;               // TMA box extent (in input pixels) must be <= 256
         for (int kx = 1; kx <= cols; ++kx) {                   // kx tiles across, balanced widths
             const int w_ = (int)ceil_div(cols, kx);
             if (w_ > max_side || w_ > kMaxN) continue;
+            if (kx > 1 && w_ == (int)ceil_div(cols, kx - 1)) continue;
             int hmax = kMaxN / w_;
             if (hmax > rows) hmax = rows;
             if (hmax > max_side) hmax = max_side;
             if (hmax < 1) continue;
-            const int ky = (int)ceil_div(rows, hmax);
-            const int h_ = (int)ceil_div(rows, ky);            // balanced heights
-            int n_ = 1;
-            if (w_ >= cols && h_ >= rows) {                    // whole image fits: stack samples
-                n_ = kMaxN / (w_ * h_);
-                if (n_ > g->batch) n_ = g->batch;
-                if (n_ < 1) n_ = 1;
-                n_ = (int)ceil_div(g->batch, ceil_div(g->batch, n_));
+            const int ky0 = (int)ceil_div(rows, hmax);
+            for (int ky = ky0; ky <= ky0 + (by_waves ? 6 : 0) && ky <= rows; ++ky) {
+                const int h_ = (int)ceil_div(rows, ky);        // balanced heights
+                int n_ = 1;
+                if (w_ >= cols && h_ >= rows) {                // whole image fits: stack samples
+                    n_ = kMaxN / (w_ * h_);
+                    if (n_ > g->batch) n_ = g->batch;
+                    if (n_ < 1) n_ = 1;
+                    n_ = (int)ceil_div(g->batch, ceil_div(g->batch, n_));
+                }
+                const int n_mma = ((w_ * h_ * n_ + 15) / 16) * 16;
+                // padded MMA work, with a mild penalty on narrow tiles (weights are re-streamed per tile)
+                const long long tiles = ceil_div(cols, w_) * ceil_div(rows, h_) * ceil_div(g->batch, n_);
+                double cost = (double)tiles * (n_mma + 32.0);
+                if (by_waves && tiles * outer >= kNumSMs)
+                    cost = (double)ceil_div(tiles * outer, kNumSMs) * kNumSMs / (double)outer * (n_mma + 32.0);
+                if (best < 0 || cost < best - 1e-9) best = cost, tw = w_, th = h_, nb = n_;
             }
-            const int n_mma = ((w_ * h_ * n_ + 15) / 16) * 16;
-            // padded MMA work, with a mild penalty on narrow tiles (weights are re-streamed per tile)
-            const double cost = (double)(ceil_div(cols, w_) * ceil_div(rows, h_) * ceil_div(g->batch, n_)) *
-                                (n_mma + 32.0);
-            if (best < 0 || cost < best - 1e-9) best = cost, tw = w_, th = h_, nb = n_;
         }
     };
     int nb_common = 1 << 30;
