@@ -165,8 +165,15 @@ def run_ours(args):
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
     lib = _lib.lib()
-    size, batch = 256, 2
-    cfg = AdaptConfig(size=size, batch=batch, warmup_iter=0, fisher_freq=50, num_fisher_img=5, fisher_quantile=40.0,
+    # default: BASELINE configs[1] (the metric's configuration).  --workload ffhq1024: configs[4], the 1024 px architecture
+    # at per-GPU batch 8 under DDP; no Fisher round in it (the reference hard-codes 256 px there, train:237, 281, 336)
+    big = args.workload == "ffhq1024"
+    size, batch = (1024, 8) if big else (256, 2)
+    n_shots = 16 if big else 10
+    workload = "stylegan2_ffhq1024_adapt_b8_per_gpu_ddp_no_fisher" if big else WORKLOAD
+    if big:
+        args.quick = True
+    cfg = AdaptConfig(size=size, batch=batch, warmup_iter=0, fisher_freq=10 ** 9 if big else 50, num_fisher_img=5, fisher_quantile=40.0,
                       prune_quantile=0.1, d_reg_every=16, g_reg_every=4, mixing=0.9, lr=0.002)
     G, D, Ge, De = build_networks(size, device, seed=1)       # identical weights on every rank (DDP)
     mode = args.mode
@@ -177,15 +184,15 @@ def run_ours(args):
         adapter = GraphedRickAdapter(cfg, G, D, Ge, De, fused_generator=True)
     else:
         adapter = RickAdapter(cfg, G, D, Ge, De, fused_generator=True)
-    shots_host = synthetic_shots(10, size, seed=100 + rank).pin_memory()
+    shots_host = synthetic_shots(n_shots, size, seed=100 + rank).pin_memory()
     shots_dev = shots_host.to(device)
     fisher_lat = torch.randn(cfg.num_fisher_img, 512, generator=torch.Generator().manual_seed(7)).to(device)
     draws = DrawStream(1234 + rank, device, cpu_seeded=False)
 
     def iteration(i, e2e):
-        if i % cfg.fisher_freq == 0:
+        if i % cfg.fisher_freq == 0 and not big:
             adapter.fisher_round(fisher_lat, shots_dev[:cfg.num_fisher_img])
-        j = (i * batch) % 10
+        j = (i * batch) % n_shots
         if e2e:
             real = shots_host[j:j + batch].to(device, non_blocking=True)          # H2D from pinned memory
         else:
@@ -223,7 +230,7 @@ def run_ours(args):
     try:
         if mode == "graphs":                      # capture every graph before iteration 0
             adapter._real.copy_(shots_dev[:batch])
-            adapter.prepare()                     # capture leaves weights / optimiser state / RNG untouched
+            adapter.prepare(fisher=not big)       # capture leaves weights / optimiser state / RNG untouched
         for i in range(W):
             iteration(i, False)
     except Exception as exc:                       # graph capture refused: fall back to the eager executor, say so
@@ -253,10 +260,10 @@ def run_ours(args):
         "optimizer_iterations_per_s": K / (ms / 1e3),
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "size": 256, "batch_per_gpu": batch, "global_batch": batch * world,
+        "config": {"workload": workload, "size": size, "batch_per_gpu": batch, "global_batch": batch * world,
                    "parallelism": f"dp{world}", "conv_math": "tf32 (fp32 storage, fp32 accumulate)",
                    "value_is": "rank-iterations per second: N ranks x optimiser iterations/s, each rank on its own "
-                               "batch-2 shots (weak scaling)",
+                               f"batch-{batch} shots (weak scaling)",
                    "exec_mode": mode,
                    "timing": "inputs regenerated on device every step (fresh latents/noise); activations + weights "
                              "(~1.5 GB/iter) exceed L2",
@@ -271,12 +278,14 @@ def run_ours(args):
     extra = {}
     # Fisher round (5 images sharded over ranks + one all-reduce of the grad^2 accumulators + masks), every N
     rdist.barrier()
-    fisher_ms = time_fisher_round(adapter, fisher_lat, shots_dev)
-    if world > 1:
-        t = torch.tensor([fisher_ms], device=device)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        fisher_ms = float(t.item())
-    extra["fisher_round_ms"] = fisher_ms
+    if not big:
+        fisher_ms = time_fisher_round(adapter, fisher_lat, shots_dev)
+        if world > 1:
+            t = torch.tensor([fisher_ms], device=device)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            fisher_ms = float(t.item())
+        extra["fisher_round_ms"] = fisher_ms
+    extra["samples_per_s"] = value * batch
     if not args.quick:
         # BASELINE config 3 as specified: 5000 samples at batch 64, sharded over the ranks (gan_training/eval.py:31-46),
         # every image copied to host memory, feature statistics all-reduced once at the end
@@ -384,7 +393,11 @@ def roofline_upfirdn2d(device):
 
 
 def op_sweep(device):
-    """BASELINE configs[3]: achieved algorithmic GB/s of the memory-bound ops (fwd / bwd), fp32."""
+    """BASELINE configs[3], all of it: achieved ALGORITHMIC GB/s of the memory-bound ops on (32, 512, r, r) tensors --
+    upfirdn2d up = 2 (forward, and its gradient = the decimating adjoint), the blur after the transposed convolution,
+    D's two blurs, and fused_leaky_relu forward / backward (backward includes grad_bias) for r = 4 ... 128 (R up to 256),
+    fp32 and bf16 storage -- plus the 12 x 12 augmentation taps, the optimiser step and the channels-last variants the
+    adaptation loop runs.  Each call is replayed from a CUDA graph between the events, L2 flushed before it."""
     from rick_b200 import op
     out = {}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
@@ -392,32 +405,42 @@ def op_sweep(device):
     taps4 = torch.outer(taps, taps) / 64 * 4
     taps1 = torch.outer(taps, taps) / 64
     n, c = 32, 512
-    for r in (16, 64, 128):
-        x = torch.randn(n, c, r, r, device=device)
-        ms = _time_kernel(lambda: op.upfirdn2d(x, taps4, up=2, pad=(2, 1)), flush, iters=5)
-        out[f"upfirdn2d_up2_{r}->{2 * r}"] = 4 * n * c * 5 * r * r / ms / 1e6
-        xb = torch.randn(n, c, 2 * r + 1, 2 * r + 1, device=device) if r <= 64 else None
-        if xb is not None:
-            ms = _time_kernel(lambda: op.upfirdn2d(xb, taps4, pad=(1, 1)), flush, iters=5)
-            out[f"blur_{2 * r + 1}->{2 * r}"] = 4 * n * c * ((2 * r + 1) ** 2 + 4 * r * r) / ms / 1e6
+
+    def rate(fn, nbytes, iters=5):
+        return nbytes / _time_kernel(fn, flush, iters=iters) / 1e6
+
+    for dtype, tag, esz in ((torch.float32, "", 4), (torch.bfloat16, "bf16_", 2)):
+        for r in (4, 8, 16, 32, 64, 128):
+            x = torch.randn(n, c, r, r, device=device, dtype=dtype)
+            out[f"{tag}upfirdn2d_up2_{r}->{2 * r}"] = rate(lambda: op.upfirdn2d(x, taps4, up=2, pad=(2, 1)),
+                                                           esz * n * c * 5 * r * r)
+            xr = x.clone().requires_grad_(True)
+            y = op.upfirdn2d(xr, taps4, up=2, pad=(2, 1))
+            go = torch.randn_like(y)
+            out[f"{tag}upfirdn2d_up2_bwd_{2 * r}->{r}"] = rate(lambda: torch.autograd.grad(y, xr, go, retain_graph=True),
+                                                              esz * n * c * 5 * r * r)
+            del xr, y, go
+            xb = torch.randn(n, c, 2 * r + 1, 2 * r + 1, device=device, dtype=dtype)
+            out[f"{tag}blur_{2 * r + 1}->{2 * r}"] = rate(lambda: op.upfirdn2d(xb, taps4, pad=(1, 1)),
+                                                         esz * n * c * ((2 * r + 1) ** 2 + 4 * r * r))
             del xb
+            out[f"{tag}d_blur_pad22_{r}->{r + 1}"] = rate(lambda: op.upfirdn2d(x, taps1, pad=(2, 2)),
+                                                         esz * n * c * (r * r + (r + 1) ** 2))
+            out[f"{tag}d_blur_pad11_{r}->{r - 1}"] = rate(lambda: op.upfirdn2d(x, taps1, pad=(1, 1)),
+                                                         esz * n * c * (r * r + (r - 1) ** 2))
+            del x
+        x = torch.randn(n, c, 128, 128, device=device, dtype=dtype)
+        out[f"{tag}down2_128->64"] = rate(lambda: op.upfirdn2d(x, taps1, down=2, pad=(1, 1)), esz * n * c * (128 * 128 + 64 * 64))
         del x
-    x = torch.randn(n, c, 128, 128, device=device)
-    ms = _time_kernel(lambda: op.upfirdn2d(x, taps1, pad=(2, 2)), flush, iters=5)
-    out["d_blur_pad22_128->129"] = 4 * n * c * (128 * 128 + 129 * 129) / ms / 1e6
-    ms = _time_kernel(lambda: op.upfirdn2d(x, taps1, down=2, pad=(1, 1)), flush, iters=5)
-    out["down2_128->64"] = 4 * n * c * (128 * 128 + 64 * 64) / ms / 1e6
-    del x
-    # bf16 storage (fp32 accumulate): same element counts, half the bytes
-    xh = torch.randn(n, c, 128, 128, device=device, dtype=torch.bfloat16)
-    ms = _time_kernel(lambda: op.upfirdn2d(xh, taps4, up=2, pad=(2, 1)), flush, iters=5)
-    out["bf16_upfirdn2d_up2_128->256"] = 2 * n * c * 5 * 128 * 128 / ms / 1e6
-    ms = _time_kernel(lambda: op.upfirdn2d(xh, taps1, pad=(2, 2)), flush, iters=5)
-    out["bf16_d_blur_pad22_128->129"] = 2 * n * c * (128 * 128 + 129 * 129) / ms / 1e6
-    bh = torch.randn(c, device=device, dtype=torch.bfloat16)
-    ms = _time_kernel(lambda: op.fused_leaky_relu(xh, bh), flush, iters=5)
-    out["bf16_bias_act_fwd_128"] = 2 * 2 * xh.numel() / ms / 1e6
-    del xh
+        bias = torch.randn(c, device=device, dtype=dtype)
+        for r in (4, 8, 16, 32, 64, 128, 256):
+            xa = torch.randn(n, c, r, r, device=device, dtype=dtype)
+            out[f"{tag}bias_act_fwd_{r}"] = rate(lambda: op.fused_leaky_relu(xa, bias), esz * 2 * xa.numel())
+            y = op.fused_leaky_relu(xa, bias)
+            go = torch.randn_like(y)
+            from rick_b200.op.fused_act import FusedLeakyReLUFunctionBackward as _Bwd
+            out[f"{tag}bias_act_bwd_{r}"] = rate(lambda: _Bwd.apply(go, y, 0.2, 2 ** 0.5), esz * 3 * xa.numel())
+            del xa, y, go
     # the 12x12 antialiasing filter of non_leaking.py:338, 359 (generic kernel; small, latency-bound tensors)
     sym6 = torch.tensor([0.015404109327027373, 0.0034907120842174702, -0.11799011114819057, -0.048311742585633,
                          0.4910559419267466, 0.787641141030194, 0.3379294217276218, -0.07263752278646252,
@@ -456,18 +479,6 @@ def op_sweep(device):
     ms = _time_kernel(lambda: torch.autograd.grad(y, [xr, br], go, retain_graph=True), flush, iters=5)
     out["bias_act_bwd_nhwc_128"] = 4 * 3 * xcl.numel() / ms / 1e6
     del xcl, xr, y, go
-    b = torch.randn(c, device=device)
-    for r in (16, 128):
-        xa = torch.randn(n, c, r, r, device=device)
-        ms = _time_kernel(lambda: op.fused_leaky_relu(xa, b), flush, iters=5)
-        out[f"bias_act_fwd_{r}"] = 4 * 2 * xa.numel() / ms / 1e6
-        xr = xa.clone().requires_grad_(True)
-        br = b.clone().requires_grad_(True)
-        y = op.fused_leaky_relu(xr, br)
-        go = torch.randn_like(y)
-        ms = _time_kernel(lambda: torch.autograd.grad(y, [xr, br], go, retain_graph=True), flush, iters=5)
-        out[f"bias_act_bwd_{r}"] = 4 * 3 * xa.numel() / ms / 1e6
-        del xa, xr, y, go
     return {k: round(v, 1) for k, v in out.items()}
 
 
@@ -691,6 +702,9 @@ def main():
                     help="iteration executor: CUDA graphs (single GPU) or eager; auto = graphs when N == 1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cuda-profiler", action="store_true", help="bracket the timed steps with cudaProfilerStart/Stop")
+    ap.add_argument("--workload", default="rick256", choices=["rick256", "ffhq1024"],
+                    help="rick256: BASELINE configs[1] (default, the metric's configuration); ffhq1024: configs[4], the "
+                         "1024 px architecture at per-GPU batch 8 under DDP")
     ap.add_argument("--quick", action="store_true", help="skip the op sweep / roofline micro-benchmarks (profiler runs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

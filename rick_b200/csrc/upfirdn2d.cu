@@ -15,8 +15,10 @@
 //                     input rows; lane = output column sliding down the rows, packed FFMA2, no predicates in the loop.
 //   upfirdn2d_tiled   4x4 taps, small maps: a CTA stages an input halo tile (several planes for tiny feature maps) in
 //                     shared memory with coalesced loads and implicit zero padding; 4 x OY outputs per thread.
+//   upfirdn2d_sep     5 .. 16 taps per axis, up / down in {1, 2} (the 12x12 antialiasing filter of non_leaking.py): the
+//                     CTA factors the outer-product kernel itself and runs two 1-D passes through shared memory.
 //   upfirdn2d_generic any taps / factors / minor: one thread per output sample, taps staged in shared memory, only
-//                     the taps that land on real samples are visited (the 12x12 taps of non_leaking.py).
+//                     the taps that land on real samples are visited.
 // All are HBM-bound by design: 4 B read per input + 4 B written per output sample (fp32); what limited the earlier
 // versions was instruction issue, see the notes at each kernel.
 #include <algorithm>
@@ -99,6 +101,170 @@ __global__ void __launch_bounds__(256) upfirdn2d_generic(UpfirdnParams p) {
             }
         }
         Elem<T>::st(static_cast<T*>(p.out) + i, acc);
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// separable tiled kernel: long FIR taps (5 .. 16 per axis), up / down in {1, 2}
+// --------------------------------------------------------------------------------------------------------
+// The only long filters on the path are outer products (non_leaking.py:321-323 builds its 12 x 12 antialiasing kernel as
+// ger(k, k)), so a 144-tap gather per output is 6x the arithmetic the filter needs.  Each CTA factors the taps itself
+// (pivot row / column of the staged 2-D kernel, verified to ~3 ulp of the pivot: no host round trip, no workspace),
+// stages the input window of a 32 x 64 output tile in shared memory with the padding zero-filled, filters along x into
+// a second shared tile and along y into the output.  Both passes give a thread 4 consecutive outputs ALONG the filtered
+// axis, so its input window lives in registers and is shared by the 4; the polyphase structure (which taps meet which
+// window element) is resolved at compile time from <UP, DOWN, KT> and the pad phase <C>, taps sit in registers.
+// Kernels that are not rank 1 take a plain 2-D loop over the same staged window.
+template <int UP, int DOWN, int KT>
+struct SepCfg {
+    static constexpr int TW = 64, TH = 32, R = 4;
+    static constexpr int ITH = ((TH - 1) * DOWN + KT - 1) / UP + 2;   // staged input rows / columns per tile
+    static constexpr int ITW = ((TW - 1) * DOWN + KT - 1) / UP + 2;
+    static constexpr int ITWP = ITW | 1;                              // odd pitch: lanes that walk down a column
+    static constexpr int TWP = TW + 1;                                //            hit 32 different banks
+    static constexpr int WIN = ((R - 1) * DOWN + KT - 1) / UP + 1;    // window of 4 consecutive outputs
+    static constexpr int STEP = R * DOWN / UP;                        // window shift between neighbouring groups
+    static constexpr size_t smem_bytes = (size_t)(ITH * ITWP + ITH * TWP) * sizeof(float);
+};
+
+// acc[j] = sum_w win[w] * k[C + w*UP - j*DOWN]   (taps outside [0, KT) do not exist)
+template <int UP, int DOWN, int KT, int C>
+__device__ __forceinline__ void sep_fir4(const float (&win)[SepCfg<UP, DOWN, KT>::WIN], const float (&k)[KT], float (&acc)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int w = 0; w < SepCfg<UP, DOWN, KT>::WIN; ++w) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int t = C + w * UP - j * DOWN;
+            if (t >= 0 && t < KT) acc[j] = fmaf(win[w], k[t], acc[j]);
+        }
+    }
+}
+
+template <typename T, int UP, int DOWN, int KT, int CX, int CY>
+__global__ void __launch_bounds__(256) upfirdn2d_sep(UpfirdnParams p) {
+    using Cfg = SepCfg<UP, DOWN, KT>;
+    extern __shared__ float sep_smem[];
+    float* s_in = sep_smem;                                   // [ITH][ITWP]
+    float* s_tmp = sep_smem + Cfg::ITH * Cfg::ITWP;           // [ITH][TWP]
+    __shared__ float s_taps[KT * KT];                         // walking order, zero padded to KT x KT
+    __shared__ float s_u[KT], s_v[KT];
+    __shared__ int s_sep;
+    const int tid = threadIdx.x, lane = tid & 31;
+
+    for (int i = tid; i < KT * KT; i += 256) {
+        const int ty = i / KT, tx = i - ty * KT;
+        float v = 0.f;
+        if (ty < p.kh && tx < p.kw) {
+            const int ky = p.flip ? ty : p.kh - 1 - ty, kx = p.flip ? tx : p.kw - 1 - tx;
+            v = __ldg(p.taps + ky * p.kw + kx);
+        }
+        s_taps[i] = v;
+    }
+    __syncthreads();
+    if (tid < 32) {                                           // rank-1 factorisation around the largest tap
+        float best = -1.f;
+        int bi = 0;
+        for (int i = lane; i < KT * KT; i += 32) {
+            const float a = fabsf(s_taps[i]);
+            if (a > best) best = a, bi = i;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) best = ob, bi = oi;
+        }
+        const int pr = bi / KT, pc = bi - pr * KT;
+        const float piv = s_taps[bi];
+        if (lane < KT) {
+            s_u[lane] = s_taps[lane * KT + pc];
+            s_v[lane] = best > 0.f ? s_taps[pr * KT + lane] / piv : 0.f;
+        }
+        __syncwarp();
+        float err = 0.f;
+        for (int i = lane; i < KT * KT; i += 32) err = fmaxf(err, fabsf(s_taps[i] - s_u[i / KT] * s_v[i % KT]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) err = fmaxf(err, __shfl_xor_sync(0xffffffffu, err, o));
+        if (lane == 0) s_sep = err <= 4e-7f * best ? 1 : 0;
+    }
+
+    // tile of this CTA
+    int b = blockIdx.x;
+    const int tx_i = b % p.tiles_x;
+    b /= p.tiles_x;
+    const int ty_i = b % p.tiles_y;
+    const long long plane = b / p.tiles_y;
+    const int ox0 = tx_i * Cfg::TW, oy0 = ty_i * Cfg::TH;
+    // first staged input column / row: the sample tap CX (CY) of the tile's first output lands on (exact division)
+    const int ix0 = (ox0 * DOWN - p.pad_x0 + CX) / UP, iy0 = (oy0 * DOWN - p.pad_y0 + CY) / UP;
+    const T* src = static_cast<const T*>(p.in) + plane * p.in_h * (long long)p.in_w;
+    for (int i = tid; i < Cfg::ITH * Cfg::ITW; i += 256) {
+        const int r = i / Cfg::ITW, c = i - r * Cfg::ITW;
+        const int iy = iy0 + r, ix = ix0 + c;
+        float v = 0.f;
+        if (iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w) v = Elem<T>::ld(src + (long long)iy * p.in_w + ix);
+        s_in[r * Cfg::ITWP + c] = v;
+    }
+    __syncthreads();
+    T* dst = static_cast<T*>(p.out) + plane * p.out_h * (long long)p.out_w;
+
+    if (s_sep) {
+        float k[KT];
+        // pass 1, along x: item = (row r, group of 4 outputs); lanes run down the rows
+#pragma unroll
+        for (int i = 0; i < KT; ++i) k[i] = s_v[i];
+        for (int i = tid; i < Cfg::ITH * (Cfg::TW / 4); i += 256) {
+            const int g = i / Cfg::ITH, r = i - g * Cfg::ITH;
+            float win[Cfg::WIN], acc[4];
+            const float* row = s_in + r * Cfg::ITWP + g * Cfg::STEP;
+#pragma unroll
+            for (int w = 0; w < Cfg::WIN; ++w) win[w] = (g * Cfg::STEP + w < Cfg::ITW) ? row[w] : 0.f;
+            sep_fir4<UP, DOWN, KT, CX>(win, k, acc);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s_tmp[r * Cfg::TWP + g * 4 + j] = acc[j];
+        }
+        __syncthreads();
+        // pass 2, along y: item = (output column, group of 4 output rows); lanes run along the columns
+#pragma unroll
+        for (int i = 0; i < KT; ++i) k[i] = s_u[i];
+        for (int i = tid; i < Cfg::TW * (Cfg::TH / 4); i += 256) {
+            const int g = i / Cfg::TW, c = i - g * Cfg::TW;
+            float win[Cfg::WIN], acc[4];
+            const float* col = s_tmp + (g * Cfg::STEP) * Cfg::TWP + c;
+#pragma unroll
+            for (int w = 0; w < Cfg::WIN; ++w) win[w] = (g * Cfg::STEP + w < Cfg::ITH) ? col[w * Cfg::TWP] : 0.f;
+            sep_fir4<UP, DOWN, KT, CY>(win, k, acc);
+            const int ox = ox0 + c;
+            if (ox < p.out_w) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int oy = oy0 + g * 4 + j;
+                    if (oy < p.out_h) Elem<T>::st(dst + (long long)oy * p.out_w + ox, acc[j]);
+                }
+            }
+        }
+    } else {
+        // not an outer product: 2-D sum over the staged window (same tap / window correspondence, run-time indices)
+        for (int i = tid; i < Cfg::TW * Cfg::TH; i += 256) {
+            const int oyl = i / Cfg::TW, oxl = i - oyl * Cfg::TW;
+            const int gy = oyl >> 2, jy = oyl & 3, gx = oxl >> 2, jx = oxl & 3;
+            float acc = 0.f;
+            for (int wy = 0; wy < Cfg::WIN; ++wy) {
+                const int ty = CY + wy * UP - jy * DOWN, r = gy * Cfg::STEP + wy;
+                if (ty < 0 || ty >= KT || r >= Cfg::ITH) continue;
+                for (int wx = 0; wx < Cfg::WIN; ++wx) {
+                    const int tx = CX + wx * UP - jx * DOWN, c = gx * Cfg::STEP + wx;
+                    if (tx < 0 || tx >= KT || c >= Cfg::ITW) continue;
+                    acc = fmaf(s_in[r * Cfg::ITWP + c], s_taps[ty * KT + tx], acc);
+                }
+            }
+            const int oy = oy0 + oyl, ox = ox0 + oxl;
+            if (oy < p.out_h && ox < p.out_w) Elem<T>::st(dst + (long long)oy * p.out_w + ox, acc);
+        }
     }
 }
 
@@ -655,6 +821,58 @@ static int launch_generic(const UpfirdnParams& p, cudaStream_t stream) {
     return RICK_OK;
 }
 
+template <typename T, int UP, int DOWN, int KT, int CX, int CY>
+static int launch_sep_c(UpfirdnParams p, cudaStream_t stream) {
+    using Cfg = SepCfg<UP, DOWN, KT>;
+    p.tiles_x = (int)ceil_div(p.out_w, Cfg::TW);
+    p.tiles_y = (int)ceil_div(p.out_h, Cfg::TH);
+    const long long blocks = (long long)p.tiles_x * p.tiles_y * p.planes;
+    if (blocks > 0x7fffffffLL) return RICK_ERR_OVERFLOW;
+    auto kernel = upfirdn2d_sep<T, UP, DOWN, KT, CX, CY>;
+    static bool attr_done[64] = {};
+    int dev = 0;
+    RICK_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {       // once per device and instantiation (graph capture friendly)
+        RICK_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
+    }
+    kernel<<<(unsigned)blocks, 256, Cfg::smem_bytes, stream>>>(p);
+    RICK_CHECK_LAUNCH();
+    return RICK_OK;
+}
+
+template <typename T, int UP, int DOWN, int KT>
+static int launch_sep_k(const UpfirdnParams& p, cudaStream_t stream) {
+    if (UP == 1) return launch_sep_c<T, UP, DOWN, KT, 0, 0>(p, stream);
+    const int cx = floor_mod(p.pad_x0, UP), cy = floor_mod(p.pad_y0, UP);     // first tap that meets a sample
+    if (cx == 0 && cy == 0) return launch_sep_c<T, UP, DOWN, KT, 0, 0>(p, stream);
+    if (cx == 1 && cy == 0) return launch_sep_c<T, UP, DOWN, KT, (UP > 1 ? 1 : 0), 0>(p, stream);
+    if (cx == 0 && cy == 1) return launch_sep_c<T, UP, DOWN, KT, 0, (UP > 1 ? 1 : 0)>(p, stream);
+    return launch_sep_c<T, UP, DOWN, KT, (UP > 1 ? 1 : 0), (UP > 1 ? 1 : 0)>(p, stream);
+}
+
+// long taps (5 .. 16 per axis) on NCHW planes with up / down in {1, 2}: the separable tiled kernel; -1 = not covered
+template <typename T>
+static int launch_sep(const UpfirdnParams& p, cudaStream_t stream) {
+    if (p.minor != 1 || p.up_x != p.up_y || p.down_x != p.down_y) return -1;
+    const int k = p.kh > p.kw ? p.kh : p.kw;
+    if (k < 5 || k > 16) return -1;
+    const int up = p.up_x, down = p.down_x;
+    if (!((up == 1 && down == 1) || (up == 2 && down == 1) || (up == 1 && down == 2))) return -1;
+    if (p.out_w < 16 || p.out_h < 8) return -1;            // tiny maps: the gather kernel has less to stage
+#define RICK_SEP(UP_, DOWN_)                                                                    \
+    if (up == UP_ && down == DOWN_) {                                                           \
+        if (k <= 8) return launch_sep_k<T, UP_, DOWN_, 8>(p, stream);                           \
+        if (k <= 12) return launch_sep_k<T, UP_, DOWN_, 12>(p, stream);                         \
+        return launch_sep_k<T, UP_, DOWN_, 16>(p, stream);                                      \
+    }
+    RICK_SEP(1, 1)
+    RICK_SEP(2, 1)
+    RICK_SEP(1, 2)
+#undef RICK_SEP
+    return -1;
+}
+
 template <typename T>
 static int dispatch(UpfirdnParams p, cudaStream_t stream) {
     // 128-bit output stores need a 16-byte aligned base (rows are then aligned whenever out_w % 4 == 0)
@@ -662,7 +880,10 @@ static int dispatch(UpfirdnParams p, cudaStream_t stream) {
                           p.pad_x0 > -64 && p.pad_y0 > -64 && aligned_to(p.out, 16) &&
                           ((p.up_x == 1 && p.down_x == 1) || (p.up_x == 2 && p.down_x == 1) ||
                            (p.up_x == 1 && p.down_x == 2));
-    if (!tiled_ok) return launch_generic<T>(p, stream);
+    if (!tiled_ok) {
+        const int rc = launch_sep<T>(p, stream);
+        return rc >= 0 ? rc : launch_generic<T>(p, stream);
+    }
     const int up = p.up_x;
     p.qx = floor_div(p.pad_x0, up);
     p.qy = floor_div(p.pad_y0, up);

@@ -98,6 +98,43 @@ def test_upfirdn2d_rows_kernel_asymmetric_taps(shape, dtype, op):
     _close(gg.float(), gw, rel)
 
 
+LONG_TAPS = [
+    # (N, C, H, W, kh, kw, up, down, pad, separable): the separable tiled kernel (5..16 taps per axis, up/down in {1,2})
+    (2, 3, 70, 90, 12, 12, 2, 1, (6, 5), True), (2, 3, 141, 77, 12, 12, 1, 2, (5, 5), True),
+    (1, 2, 64, 64, 12, 12, 1, 1, (3, 8), True), (1, 2, 33, 130, 7, 11, 2, 1, (3, 2), True),
+    (1, 2, 50, 41, 16, 5, 1, 2, (7, 0), True), (1, 3, 40, 40, 12, 12, 2, 1, (-3, 9), True),
+    (1, 2, 45, 67, 12, 12, 2, 1, (6, 5), False), (1, 2, 90, 70, 9, 9, 1, 2, (4, 4), False),
+    (1, 1, 100, 100, 6, 6, 1, 1, (-2, -1), False), (2, 3, 282, 282, 12, 12, 2, 1, (0, 0), True),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("case", LONG_TAPS, ids=[f"{c[2]}x{c[3]}_k{c[4]}x{c[5]}_u{c[6]}d{c[7]}_{'sep' if c[9] else '2d'}" for c in LONG_TAPS])
+def test_upfirdn2d_long_taps_separable_kernel(case, dtype, op):
+    """non_leaking.py:321-359 (12 x 12 outer-product antialiasing taps, up = 2 / down = 2) and other long filters: rank-1
+    kernels go through the in-kernel factorisation + two 1-D passes, anything else through the 2-D loop of the same
+    kernel; forward and the gradient (the adjoint runs the flipped taps with up <-> down)."""
+    n, c, h, w, kh, kw, up, down, pad, sep = case
+    g = torch.Generator().manual_seed(kh * 100 + kw + h)
+    x = torch.randn(n, c, h, w, generator=g)
+    if sep:
+        taps = torch.outer(torch.randn(kh, generator=g), torch.randn(kw, generator=g))
+    else:
+        taps = torch.randn(kh, kw, generator=g)
+    rel = REL if dtype == torch.float32 else 2e-2
+    xo = x.to(dtype).float().requires_grad_(True)
+    want = ops.upfirdn2d(xo, taps, up, down, pad)
+    xg = x.to(dtype).cuda().requires_grad_(True)
+    got = op.upfirdn2d(xg, taps.cuda(), up, down, pad)
+    assert tuple(got.shape) == tuple(want.shape) and got.dtype == dtype
+    _close(got.float(), want.detach(), rel)
+    if dtype == torch.float32:
+        go = torch.randn(want.shape, generator=g)
+        (gw,) = torch.autograd.grad(want, xo, go)
+        (gg,) = torch.autograd.grad(got, xg, go.cuda())
+        _close(gg, gw, rel)
+
+
 def test_upfirdn2d_double_backward(op):
     g = torch.Generator().manual_seed(5)
     x = torch.randn(2, 3, 12, 12, generator=g)
