@@ -346,21 +346,17 @@ def _flush_l2(buf):
 def _time_kernel(fn, flush_buf, iters=10, warm=3, graph=True):
     """average device time of fn() in ms: CUDA events on the launching stream, L2 flushed before every launch.  The call
     is replayed from a CUDA graph (as the timed iteration replays it), so the Python / ctypes / autograd dispatch of
-    ``fn`` -- 20-50 us, more than a small-map kernel takes -- is not inside the events; eager launch when a call cannot
-    be captured."""
+    ``fn`` -- 20-50 us, more than a small-map kernel takes -- is not inside the events (``graph=False``: eager launch,
+    for calls that cannot be captured)."""
     for _ in range(warm):
         fn()
     g = None
     if graph:
         torch.cuda.synchronize()
-        try:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                keep = fn()                        # noqa: F841  (outputs live in the graph's pool until g is dropped)
-            g.replay()
-        except Exception:
-            g = None
-            torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            keep = fn()                            # noqa: F841  (outputs live in the graph's pool until g is dropped)
+        g.replay()
     times = []
     for _ in range(iters):
         _flush_l2(flush_buf)
@@ -399,6 +395,8 @@ def op_sweep(device):
     fp32 and bf16 storage -- plus the 12 x 12 augmentation taps, the optimiser step and the channels-last variants the
     adaptation loop runs.  Each call is replayed from a CUDA graph between the events, L2 flushed before it."""
     from rick_b200 import op
+    from rick_b200.op.fused_act import FusedLeakyReLUFunctionBackward as _Bwd
+    from rick_b200.op.upfirdn2d import upfirdn2d_adjoint
     out = {}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
     taps = torch.tensor([1., 3., 3., 1.], device=device)
@@ -409,17 +407,20 @@ def op_sweep(device):
     def rate(fn, nbytes, iters=5):
         return nbytes / _time_kernel(fn, flush, iters=iters) / 1e6
 
+    # what this timing method reads for a launch that does (almost) nothing: events + one graph launch around a 16-byte
+    # fill.  A 5 MB op (r = 4) cannot show more than 5 MB / floor, whatever its kernel does.
+    tiny = torch.zeros(4, device=device)
+    out["timing_floor_us"] = _time_kernel(lambda: tiny.add_(1.0), flush, iters=10) * 1e3
+
     for dtype, tag, esz in ((torch.float32, "", 4), (torch.bfloat16, "bf16_", 2)):
         for r in (4, 8, 16, 32, 64, 128):
             x = torch.randn(n, c, r, r, device=device, dtype=dtype)
             out[f"{tag}upfirdn2d_up2_{r}->{2 * r}"] = rate(lambda: op.upfirdn2d(x, taps4, up=2, pad=(2, 1)),
                                                            esz * n * c * 5 * r * r)
-            xr = x.clone().requires_grad_(True)
-            y = op.upfirdn2d(xr, taps4, up=2, pad=(2, 1))
-            go = torch.randn_like(y)
-            out[f"{tag}upfirdn2d_up2_bwd_{2 * r}->{r}"] = rate(lambda: torch.autograd.grad(y, xr, go, retain_graph=True),
-                                                              esz * n * c * 5 * r * r)
-            del xr, y, go
+            go = torch.randn(n, c, 2 * r, 2 * r, device=device, dtype=dtype)
+            out[f"{tag}upfirdn2d_up2_bwd_{2 * r}->{r}"] = rate(
+                lambda: upfirdn2d_adjoint(go, taps4, up=2, pad=(2, 1), in_size=(r, r)), esz * n * c * 5 * r * r)
+            del go
             xb = torch.randn(n, c, 2 * r + 1, 2 * r + 1, device=device, dtype=dtype)
             out[f"{tag}blur_{2 * r + 1}->{2 * r}"] = rate(lambda: op.upfirdn2d(xb, taps4, pad=(1, 1)),
                                                          esz * n * c * ((2 * r + 1) ** 2 + 4 * r * r))
@@ -438,7 +439,6 @@ def op_sweep(device):
             out[f"{tag}bias_act_fwd_{r}"] = rate(lambda: op.fused_leaky_relu(xa, bias), esz * 2 * xa.numel())
             y = op.fused_leaky_relu(xa, bias)
             go = torch.randn_like(y)
-            from rick_b200.op.fused_act import FusedLeakyReLUFunctionBackward as _Bwd
             out[f"{tag}bias_act_bwd_{r}"] = rate(lambda: _Bwd.apply(go, y, 0.2, 2 ** 0.5), esz * 3 * xa.numel())
             del xa, y, go
     # the 12x12 antialiasing filter of non_leaking.py:338, 359 (generic kernel; small, latency-bound tensors)
@@ -472,13 +472,11 @@ def op_sweep(device):
     bcl = torch.randn(c, device=device)
     ms = _time_kernel(lambda: op.fused_leaky_relu(xcl, bcl), flush, iters=5)
     out["bias_act_fwd_nhwc_128"] = 4 * 2 * xcl.numel() / ms / 1e6
-    xr = xcl.clone().requires_grad_(True)
-    br = bcl.clone().requires_grad_(True)
-    y = op.fused_leaky_relu(xr, br)
+    y = op.fused_leaky_relu(xcl, bcl)
     go = torch.randn_like(y)
-    ms = _time_kernel(lambda: torch.autograd.grad(y, [xr, br], go, retain_graph=True), flush, iters=5)
+    ms = _time_kernel(lambda: _Bwd.apply(go, y, 0.2, 2 ** 0.5), flush, iters=5)
     out["bias_act_bwd_nhwc_128"] = 4 * 3 * xcl.numel() / ms / 1e6
-    del xcl, xr, y, go
+    del xcl, y, go
     return {k: round(v, 1) for k, v in out.items()}
 
 

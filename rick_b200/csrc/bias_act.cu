@@ -247,6 +247,45 @@ __global__ void __launch_bounds__(256) bias_act_bwd_nhwc_main(float* __restrict_
     }
 }
 
+// ---- small planes (N*H*W <= 16384 per channel: the 4 .. 16 px layers, and the (B, C) outputs of the style MLP): ONE pass.
+// A channel belongs to one warp (<= 1024 elements) or one CTA; its threads walk the channel's N planes, write grad_in and
+// fold their partial sums in a fixed order, so grad_bias needs neither the partial planes nor the fold launch that cost
+// more than the pass itself at these sizes (0.15 of HBM at r = 16 in round 1).
+template <typename T>
+__global__ void __launch_bounds__(256) bias_act_bwd_small(T* __restrict__ gin, float* __restrict__ grad_bias,
+                                                          const T* __restrict__ gout, const T* __restrict__ saved, int n,
+                                                          int c, int hw, int tpc, float alpha, float scale) {
+    __shared__ float s_part[8];
+    const int per_cta = blockDim.x / tpc;
+    const int ch = blockIdx.x * per_cta + threadIdx.x / tpc;
+    const int t = threadIdx.x % tpc;
+    const int total = n * hw;
+    float acc = 0.f;
+    if (ch < c) {
+        for (int e = t; e < total; e += tpc) {
+            const int i_n = e / hw, pos = e - i_n * hw;
+            const long long idx = ((long long)i_n * c + ch) * hw + pos;
+            const float g = Elem<T>::ld(gout + idx);
+            const float r = (Elem<T>::ld(saved + idx) > 0.f ? g : g * alpha) * scale;
+            Elem<T>::st(gin + idx, r);
+            acc += r;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (tpc == 32) {
+        if (t == 0 && ch < c) grad_bias[ch] = acc;
+        return;
+    }
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0 && ch < c) {
+        float sum = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) sum += s_part[w];
+        grad_bias[ch] = sum;
+    }
+}
+
 static inline int bwd_chunks(int64_t hw_vec) { return (int)ceil_div(hw_vec, 32 * kBwdUnroll); }
 
 template <typename T>
@@ -256,6 +295,14 @@ static int launch_bias_act_bwd(void* gin, float* grad_bias, void* ws, const void
     const bool vec = (hw % N == 0) && aligned_to(gin, 16) && aligned_to(gout, 16) && aligned_to(saved, 16);
     const long long cap = (long long)kNumSMs * 16;
     const unsigned fold_blocks = (unsigned)ceil_div(c * 32, 256);
+    if (n * hw <= 16384) {                       // small planes: one pass, no partials
+        const int tpc = n * hw <= 1024 ? 32 : 256;
+        const long long blocks = ceil_div(c, 256 / tpc);
+        bias_act_bwd_small<T><<<(unsigned)blocks, 256, 0, s>>>((T*)gin, grad_bias, (const T*)gout, (const T*)saved, (int)n,
+                                                                (int)c, (int)hw, tpc, alpha, scale);
+        RICK_CHECK_LAUNCH();
+        return RICK_OK;
+    }
     if (vec) {
         const int64_t hw_vec = hw / N;
         const int chunks = bwd_chunks(hw_vec);

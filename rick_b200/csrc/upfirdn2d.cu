@@ -136,8 +136,6 @@ __device__ __forceinline__ void sep_fir4(const float (&win)[SepCfg<UP, DOWN, KT>
     for (int w = 0; w < SepCfg<UP, DOWN, KT>::WIN; ++w) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            constexpr int dummy = 0;
-            (void)dummy;
             const int t = C + w * UP - j * DOWN;
             if (t >= 0 && t < KT) acc[j] = fmaf(win[w], k[t], acc[j]);
         }
@@ -264,6 +262,100 @@ __global__ void __launch_bounds__(256) upfirdn2d_sep(UpfirdnParams p) {
             }
             const int oy = oy0 + oyl, ox = ox0 + oxl;
             if (oy < p.out_h && ox < p.out_w) Elem<T>::st(dst + (long long)oy * p.out_w + ox, acc);
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// column-walker kernel: 4x4 taps on SMALL planes (4 .. ~64 px: every layer below 64 px, any odd size)
+// --------------------------------------------------------------------------------------------------------
+// The tiled kernel gives a thread a 4 x OY patch and a CTA a power-of-two grid of them: on a 33 x 33 or 17 x 17 plane a
+// third of the threads have work and rows end off the 128-bit store grid (0.06 - 0.3 of HBM in the round-2 op sweep).
+// Here a thread owns ONE output column of one plane and walks down it: the 4 x 4 input window lives in registers and
+// takes DOWN new rows per output (4 or 8 loads, straight from global memory -- neighbouring lanes read neighbouring
+// samples and the three neighbours that share each sample hit L1), 16 FMAs, one store; lanes run along (plane, column)
+// pairs in linear order, so every thread has work whatever the plane's size and a warp's loads / stores are contiguous
+// runs.  No shared memory, no barrier, no per-output index arithmetic.  up = 2 needs no window: 2 x 2 taps per output.
+template <typename T, int UP, int DOWN>
+__global__ void __launch_bounds__(256) upfirdn2d_cols(UpfirdnParams p) {
+    __shared__ float s_taps[16];
+    const int tid = threadIdx.x;
+    if (tid < 16) {
+        const int ty = tid >> 2, tx = tid & 3;
+        const int ky = p.flip ? ty : 3 - ty, kx = p.flip ? tx : 3 - tx;
+        s_taps[tid] = __ldg(p.taps + ky * 4 + kx);
+    }
+    __syncthreads();
+    const long long items = p.planes * p.out_w;
+    const long long in_px = (long long)p.in_h * p.in_w, out_px = (long long)p.out_h * p.out_w;
+    for (long long it = blockIdx.x * 256LL + tid; it < items; it += gridDim.x * 256LL) {
+        const long long plane = it / p.out_w;
+        const int ox = (int)(it - plane * p.out_w);
+        const T* __restrict__ src = static_cast<const T*>(p.in) + plane * in_px;
+        T* __restrict__ dst = static_cast<T*>(p.out) + plane * out_px + ox;
+        if (UP == 1) {
+            float w[4][4];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) w[i >> 2][i & 3] = s_taps[i];
+            const int ix0 = ox * DOWN - p.pad_x0;                  // column under tap 0
+            bool okx[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) okx[b] = ix0 + b >= 0 && ix0 + b < p.in_w;
+            float win[4][4];
+            int iy = -p.pad_y0;                                    // row under tap 0 of output row 0
+#pragma unroll
+            for (int a = DOWN; a < 4; ++a) {                       // rows the first output shares with its "predecessor"
+                const int y = iy + a - DOWN;
+                const bool oky = y >= 0 && y < p.in_h;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) win[a][b] = (oky && okx[b]) ? Elem<T>::ld(src + (long long)y * p.in_w + ix0 + b) : 0.f;
+            }
+            // (unrolled so that the loads of the next rows are issued before this row's FMAs and store retire)
+#pragma unroll 4
+            for (int oy = 0; oy < p.out_h; ++oy, iy += DOWN) {
+#pragma unroll
+                for (int a = 0; a < 4 - DOWN; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) win[a][b] = win[a + DOWN][b];
+#pragma unroll
+                for (int a = 4 - DOWN; a < 4; ++a) {
+                    const int y = iy + a;
+                    const bool oky = y >= 0 && y < p.in_h;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        win[a][b] = (oky && okx[b]) ? Elem<T>::ld(src + (long long)y * p.in_w + ix0 + b) : 0.f;
+                }
+                float acc = 0.f;
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc = fmaf(win[a][b], w[a][b], acc);
+                Elem<T>::st(dst + (long long)oy * p.out_w, acc);
+            }
+        } else {
+            // up = 2: taps tx0, tx0 + 2 (fixed per column) and ty0, ty0 + 2 (alternating down the column) meet samples
+            const int bx = ox * DOWN - p.pad_x0;
+            const int tx0 = bx & 1, ix = (bx + tx0) / 2;
+            const bool okx0 = ix >= 0 && ix < p.in_w, okx1 = ix + 1 >= 0 && ix + 1 < p.in_w;
+            float wc[4][2];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) wc[a][0] = s_taps[a * 4 + tx0], wc[a][1] = s_taps[a * 4 + tx0 + 2];
+#pragma unroll 4
+            for (int oy = 0; oy < p.out_h; ++oy) {
+                const int by = oy * DOWN - p.pad_y0;
+                const int ty0 = by & 1, y = (by + ty0) / 2;
+                const float w00 = ty0 ? wc[1][0] : wc[0][0], w01 = ty0 ? wc[1][1] : wc[0][1];
+                const float w10 = ty0 ? wc[3][0] : wc[2][0], w11 = ty0 ? wc[3][1] : wc[2][1];
+                const bool oky0 = y >= 0 && y < p.in_h, oky1 = y + 1 >= 0 && y + 1 < p.in_h;
+                const T* r0 = src + (long long)y * p.in_w + ix;
+                const T* r1 = r0 + p.in_w;
+                float acc = 0.f;
+                if (oky0 && okx0) acc = fmaf(Elem<T>::ld(r0), w00, acc);
+                if (oky0 && okx1) acc = fmaf(Elem<T>::ld(r0 + 1), w01, acc);
+                if (oky1 && okx0) acc = fmaf(Elem<T>::ld(r1), w10, acc);
+                if (oky1 && okx1) acc = fmaf(Elem<T>::ld(r1 + 1), w11, acc);
+                Elem<T>::st(dst + (long long)oy * p.out_w, acc);
+            }
         }
     }
 }
@@ -873,6 +965,18 @@ static int launch_sep(const UpfirdnParams& p, cudaStream_t stream) {
     return -1;
 }
 
+// column-walker kernel for 4x4 taps on small planes
+template <typename T, int UP, int DOWN>
+static int launch_cols(const UpfirdnParams& p, cudaStream_t stream) {
+    const long long items = p.planes * p.out_w;
+    long long blocks = ceil_div(items, 256);
+    const long long cap = (long long)kNumSMs * 64;
+    if (blocks > cap) blocks = cap;
+    upfirdn2d_cols<T, UP, DOWN><<<(unsigned)blocks, 256, 0, stream>>>(p);
+    RICK_CHECK_LAUNCH();
+    return RICK_OK;
+}
+
 template <typename T>
 static int dispatch(UpfirdnParams p, cudaStream_t stream) {
     // 128-bit output stores need a 16-byte aligned base (rows are then aligned whenever out_w % 4 == 0)
@@ -893,7 +997,17 @@ static int dispatch(UpfirdnParams p, cudaStream_t stream) {
         const int rc = p.down_x == 1 ? launch_rows<T, 1>(p, stream) : launch_rows<T, 2>(p, stream);
         if (rc >= 0) return rc;
     }
-    if (up == 1 && p.down_x == 1) return large ? launch_direct<T, 1, 1, 0, 0, 4>(p, stream) : launch_tiled<T, 1, 1, 0, 0, 4>(p, stream);
+    if (!large && p.planes * p.out_w >= 4096) {           // small planes, enough columns to fill the GPU: column walkers
+        if (up == 1 && p.down_x == 1) return launch_cols<T, 1, 1>(p, stream);
+        if (up == 2 && p.down_x == 1) return launch_cols<T, 2, 1>(p, stream);
+        if (up == 1 && p.down_x == 2) return launch_cols<T, 1, 2>(p, stream);
+    }
+    // tiny planes (<= 16 output rows, the 4 .. 8 px layers): 2 output rows per thread instead of 4 / 8, or a
+    // (32, 512, 4, 4) -> 8 x 8 call runs on 128 CTAs of threads that each grind through 32 outputs
+    const bool tiny = p.out_h <= 16;
+    if (up == 1 && p.down_x == 1)
+        return large ? launch_direct<T, 1, 1, 0, 0, 4>(p, stream)
+                     : (tiny ? launch_tiled<T, 1, 1, 0, 0, 2>(p, stream) : launch_tiled<T, 1, 1, 0, 0, 4>(p, stream));
     if (up == 1 && p.down_x == 2) return large ? launch_direct<T, 1, 2, 0, 0, 4>(p, stream) : launch_tiled<T, 1, 2, 0, 0, 2>(p, stream);
     if (large) {
         if (px == 0 && py == 0) return launch_direct<T, 2, 1, 0, 0, 8>(p, stream);
@@ -904,6 +1018,12 @@ static int dispatch(UpfirdnParams p, cudaStream_t stream) {
     // (an 8-wide patch per thread was measured slower: 3.94 vs 4.43 TB/s -- its two 128-bit stores per row leave every
     //  warp-wide store instruction half-covering its 32-byte sectors; 4-wide keeps each store instruction at 512
     //  contiguous bytes)
+    if (tiny) {
+        if (px == 0 && py == 0) return launch_tiled<T, 2, 1, 0, 0, 2>(p, stream);
+        if (px == 1 && py == 0) return launch_tiled<T, 2, 1, 1, 0, 2>(p, stream);
+        if (px == 0 && py == 1) return launch_tiled<T, 2, 1, 0, 1, 2>(p, stream);
+        return launch_tiled<T, 2, 1, 1, 1, 2>(p, stream);
+    }
     if (px == 0 && py == 0) return launch_tiled<T, 2, 1, 0, 0, 8>(p, stream);
     if (px == 1 && py == 0) return launch_tiled<T, 2, 1, 1, 0, 8>(p, stream);
     if (px == 0 && py == 1) return launch_tiled<T, 2, 1, 0, 1, 8>(p, stream);

@@ -90,6 +90,18 @@ def upfirdn2d(input, kernel, up=1, down=1, pad=(0, 0)):
     return UpFirDn2d.apply(input, kernel, (up, up), (down, down), (pad[0], pad[1], pad[0], pad[1]), False)
 
 
+def upfirdn2d_adjoint(grad_output, kernel, up=1, down=1, pad=(0, 0), in_size=None):
+    """The gradient of ``upfirdn2d(x, kernel, up, down, pad)`` w.r.t. ``x`` for an input of spatial size ``in_size``
+    (H, W): the same operator with up <-> down swapped, flipped taps and the pads of op/upfirdn2d.py:111-114 -- what
+    ``UpFirDn2d.backward`` launches, callable directly (benchmarks, callers that manage their own graphs)."""
+    kh, kw = kernel.shape
+    in_h, in_w = in_size
+    out_h, out_w = grad_output.shape[2:]
+    g_pad = (kw - pad[0] - 1, in_w * up - out_w * down + pad[0] - up + 1,
+             kh - pad[0] - 1, in_h * up - out_h * down + pad[0] - up + 1)
+    return UpFirDn2d.apply(grad_output, kernel, (down, down), (up, up), g_pad, True)
+
+
 def upfirdn2d_xy(input, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1):
     """The native entry point's full parameter set (op/upfirdn2d.cpp:12-19)."""
     return UpFirDn2d.apply(input, kernel, (up_x, up_y), (down_x, down_y), (pad_x0, pad_x1, pad_y0, pad_y1), False)
