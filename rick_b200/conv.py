@@ -68,7 +68,8 @@ def _cl(t: torch.Tensor) -> torch.Tensor:
     return t if _is_cl(t) else t.contiguous(memory_format=torch.channels_last)
 
 
-def _fprop(x, w, cfg):
+def _fprop(x, w, cfg, bias_act=None):
+    """``bias_act`` = (bias, slope, scale): lrelu(conv + bias) * scale from the kernel's epilogue (tcgen05 path only)."""
     stride, padding, transposed = cfg
     co, ci, k, _ = w.shape
     if _use_tc(x, w.shape, cfg, co, ci):
@@ -77,7 +78,12 @@ def _fprop(x, w, cfg):
         b, _, h, wd = x.shape
         geom = (_ct.geom_conv_transpose_s2(b, h, wd, ci, co, k) if transposed
                 else _ct.geom_conv(b, h, wd, ci, co, k, stride, padding))
+        if bias_act is not None:
+            bias, slope, scale = bias_act
+            return _nhwc_out(_ct.conv_tc_nhwc(_nhwc(x), w, geom, bias=bias.contiguous(), act=True, alpha=slope, scale=scale))
         return _nhwc_out(_ct.conv_tc_nhwc(_nhwc(x), w, geom))
+    if bias_act is not None:
+        raise RuntimeError("rick_b200.conv: fused bias + activation needs the tcgen05 path")
     launch_stats["library"] += 1
     wl = w.transpose(0, 1) if transposed else w
     return torch.ops.aten.convolution(x, wl, None, *_conv_args(*cfg))
@@ -185,6 +191,48 @@ class _ConvGrad(torch.autograd.Function):
         if need_x and ggw is not None:
             d_x = _ConvGrad.apply(g, x, ggw, True, False, *cfg)[0]
         return d_g, d_x, d_w, None, None, None, None, None
+
+
+class _ConvBiasAct(torch.autograd.Function):
+    """``fused_leaky_relu(conv(x, w), bias)`` -- ConvLayer's EqualConv2d + FusedLeakyReLU pair (model_probe_tune.py:
+    614-639) -- with bias and activation applied in the convolution kernel's epilogue: the activation map is written
+    once instead of written, re-read and re-written by a separate bias-act launch.  Backward is composed of the two
+    differentiable pieces it replaces (the bias-act backward Function on the saved OUTPUT, op/fused_act.py:19-48, and
+    ``_ConvGrad``), so first and second derivatives are those of the unfused pair."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, stride, padding, slope, scale):
+        out = _fprop(x, w, (stride, padding, False), bias_act=(bias, slope, scale))
+        ctx.save_for_backward(x, w, out)
+        ctx.cfg = (stride, padding, False)
+        ctx.act = (slope, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        from .op.fused_act import FusedLeakyReLUFunctionBackward
+        x, w, out = ctx.saved_tensors
+        need_x, need_w, need_b = ctx.needs_input_grad[:3]
+        g_pre, g_bias = FusedLeakyReLUFunctionBackward.apply(g, out, *ctx.act)
+        gx = gw = None
+        if need_x or need_w:
+            if not torch.is_grad_enabled():
+                gx = _dgrad(g_pre, w, x, ctx.cfg) if need_x else None
+                gw = _wgrad(g_pre, x, w, ctx.cfg) if need_w else None
+            else:
+                gx, gw = _ConvGrad.apply(g_pre, x, w, need_x, need_w, *ctx.cfg)
+        return gx, gw, (g_bias if need_b else None), None, None, None, None
+
+
+def conv2d_bias_act(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, stride: int, padding: int,
+                    slope: float, scale: float):
+    """EqualConv2d (no bias of its own) followed by FusedLeakyReLU, as one launch when the tcgen05 kernel covers the
+    shape; None otherwise (the caller then runs the two modules)."""
+    if not (x.is_cuda and x.dim() == 4 and bias.dtype == torch.float32):
+        return None
+    if not _use_tc(x, weight.shape, (stride, padding, False), weight.shape[0], weight.shape[1]) or _FORCE == "tc-unfused":
+        return None
+    return _ConvBiasAct.apply(x, weight, bias, stride, padding, slope, scale)
 
 
 def _lib_conv(x, w, stride: int = 1, padding: int = 0, transposed: bool = False):

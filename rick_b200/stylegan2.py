@@ -42,6 +42,7 @@ _CHANNELS_LAST = os.environ.get("RICK_CHANNELS_LAST", "1") != "0"
 _PRESCALE = os.environ.get("RICK_PRESCALE", "1") != "0"           # one multi-tensor launch for all equalised-lr multipliers
 _FUSED_STYLED = os.environ.get("RICK_FUSED_STYLED", "1") != "0"   # fused modulate / demod-noise-bias-act ops in StyledConv
 _FUSED_LINEARS = os.environ.get("RICK_FUSED_LINEARS", "1") != "0"  # mapping network / all modulation layers: one launch each
+_FUSED_CONV_ACT = os.environ.get("RICK_FUSED_CONV_ACT", "1") != "0"  # D: EqualConv2d + FusedLeakyReLU as one launch
 
 
 def set_fused_styled(flag: bool) -> None:
@@ -488,6 +489,27 @@ class ConvLayer(nn.Sequential):
         if activate:
             layers.append(FusedLeakyReLU(out_channel) if bias else ScaledLeakyReLU(0.2))
         super().__init__(*layers)
+
+    def forward(self, input):
+        """Same modules, same order; an EqualConv2d directly followed by FusedLeakyReLU runs as ONE convolution launch
+        whose epilogue adds the bias and applies the activation (rick_b200.conv.conv2d_bias_act)."""
+        mods = list(self)
+        x = input
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            nxt = mods[i + 1] if i + 1 < len(mods) else None
+            if (_FUSED_CONV_ACT and isinstance(m, EqualConv2d) and m.bias is None and isinstance(nxt, FusedLeakyReLU)
+                    and x.is_cuda and m.weight.shape[1] % 32 == 0):
+                w = m._ws if m._ws is not None else m.weight * m.scale
+                y = _conv.conv2d_bias_act(x, w, nxt.bias, m.stride, m.padding, nxt.negative_slope, nxt.scale)
+                if y is not None:
+                    x = y
+                    i += 2
+                    continue
+            x = m(x)
+            i += 1
+        return x
 
 
 class ResBlock(nn.Module):
