@@ -286,7 +286,7 @@ def run_ours(args):
             fisher_ms = float(t.item())
         extra["fisher_round_ms"] = fisher_ms
     extra["samples_per_s"] = value * batch
-    if not args.quick:
+    if not args.quick or args.samplegen:
         # BASELINE config 3 as specified: 5000 samples at batch 64, sharded over the ranks (gan_training/eval.py:31-46),
         # every image copied to host memory, feature statistics all-reduced once at the end
         from rick_b200 import sample as rsample
@@ -703,6 +703,7 @@ def main():
     ap.add_argument("--workload", default="rick256", choices=["rick256", "ffhq1024"],
                     help="rick256: BASELINE configs[1] (default, the metric's configuration); ffhq1024: configs[4], the "
                          "1024 px architecture at per-GPU batch 8 under DDP")
+    ap.add_argument("--samplegen", action="store_true", help="with --quick: still run the config-3 sample-generation loop")
     ap.add_argument("--quick", action="store_true", help="skip the op sweep / roofline micro-benchmarks (profiler runs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

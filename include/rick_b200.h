@@ -311,6 +311,20 @@ RICK_API int rick_styled_epilogue_bwd_nhwc(void* ga, float* gdemod, float* gbias
 RICK_API int rick_weight_sqsum(float* out, const float* w, int cout, int cin, int taps, int64_t stride_co,
                                int64_t stride_ci, int64_t stride_tap, rick_stream_t stream);
 
+/* Demodulation table of a ModulatedConv2d (model_probe_tune.py:246-251, algebraic form), batch <= 8:
+ *     demod[b][co] = rsqrt(scale2 * sum_ci s[b][ci]^2 * wsq[co][ci] + eps);   s_out[b][ci] = s[b][ci] * s_scale (s_out may
+ * be NULL).  rick_demod_bwd: first derivatives -- g_s[b][ci] = 2 s sum_co q wsq + s_scale g_sout (g_sout may be NULL),
+ * g_wsq[co][ci] = sum_b q s^2 with q = -0.5 demod^3 scale2 g_demod; either output may be NULL. */
+RICK_API int rick_demod_fwd(float* demod, float* s_out, const float* s, const float* wsq, int batch, int cin, int cout,
+                            float scale2, float eps, float s_scale, rick_stream_t stream);
+RICK_API int rick_demod_bwd(float* g_s, float* g_wsq, const float* g_demod, const float* g_sout, const float* demod,
+                            const float* s, const float* wsq, int batch, int cin, int cout, float scale2, float s_scale,
+                            rick_stream_t stream);
+
+/* out = (a + b) * scale over n floats (n % 4 == 0, 16-byte aligned): the residual merge of ResBlock
+ * (model_probe_tune.py:655-660, ``(out + skip) / sqrt(2)``) as one pass. */
+RICK_API int rick_add_scale(float* out, const float* a, const float* b, float scale, int64_t n, rick_stream_t stream);
+
 /* `count` small-batch EqualLinear layers in one launch (model_probe_tune.py:139-173: the 8 mapping-network layers, the
  * style -> channel modulation layer of every ModulatedConv2d):
  *     y[l][b, r] = act( w_scale[l] * sum_k w[l][r, k] * x[l][b, k] + b_scale[l] * bias[l][r] ),   b < batch <= 8

@@ -60,6 +60,10 @@ _PROTOTYPES = {
     "rick_from_rgb_bwd_data": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_float,
                                        c_int, c_float, c_float, c_void_p]),
     "rick_weight_sqsum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_void_p]),
+    "rick_demod_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_float,
+                               c_void_p]),
+    "rick_demod_bwd": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_float, c_float, c_void_p]),
+    "rick_add_scale": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int64, c_void_p]),
     "rick_adam_mask_ema": (c_int, [POINTER(c_void_p)] * 8 + [POINTER(c_int64), POINTER(c_int64), c_int,
                                    c_float, c_float, c_float, c_float, c_float, c_void_p]),
 }

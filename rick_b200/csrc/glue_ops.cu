@@ -335,3 +335,159 @@ extern "C" int rick_from_rgb_bwd_data(float* gimg, const float* g, const float* 
     RICK_CHECK_LAUNCH();
     return RICK_OK;
 }
+
+// -------------------------------------------------------------------------------------------------------------------
+// demodulation table of a ModulatedConv2d (model_probe_tune.py:246-251 in its algebraic form):
+//     demod[b][co] = rsqrt(scale2 * sum_ci s[b][ci]^2 * wsq[co][ci] + eps),     s_out[b][ci] = s[b][ci] * s_scale
+// As module code this is pow / mm / mul / add / rsqrt / mul on (B, 512) tensors: six launches per layer and pass, the mm a
+// 10 us cuBLAS GEMV (0.65 ms of a 13 ms iteration in the round-2 glue profile).  One warp per output channel here.
+// -------------------------------------------------------------------------------------------------------------------
+namespace rick {
+namespace {
+constexpr int kDemodMaxBatch = 8;
+
+__global__ void __launch_bounds__(256)
+demod_fwd_kernel(float* __restrict__ demod, float* __restrict__ s_out, const float* __restrict__ s,
+                 const float* __restrict__ wsq, int batch, int cin, int cout, float scale2, float eps, float s_scale) {
+    const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (s_out) {                                   // the scaled style: every thread of the grid takes a few elements
+        for (int i = blockIdx.x * 256 + threadIdx.x; i < batch * cin; i += gridDim.x * 256) s_out[i] = s[i] * s_scale;
+    }
+    if (warp >= cout) return;
+    float acc[kDemodMaxBatch];
+#pragma unroll
+    for (int b = 0; b < kDemodMaxBatch; ++b) acc[b] = 0.f;
+    const float* wrow = wsq + (size_t)warp * cin;
+    for (int ci = lane; ci < cin; ci += 32) {
+        const float w = __ldg(wrow + ci);
+#pragma unroll
+        for (int b = 0; b < kDemodMaxBatch; ++b)
+            if (b < batch) {
+                const float v = __ldg(s + (size_t)b * cin + ci);
+                acc[b] = fmaf(v * v, w, acc[b]);
+            }
+    }
+#pragma unroll
+    for (int b = 0; b < kDemodMaxBatch; ++b) {
+        if (b < batch) {
+            float a = acc[b];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) demod[(size_t)b * cout + warp] = rsqrtf(fmaf(a, scale2, eps));
+        }
+    }
+}
+
+// q[b][co] = -0.5 * demod^3 * scale2 * g_demod;   g_wsq[co][ci] = sum_b q[b][co] * s[b][ci]^2
+__global__ void __launch_bounds__(256)
+demod_bwd_wsq_kernel(float* __restrict__ g_wsq, const float* __restrict__ g_demod, const float* __restrict__ demod,
+                     const float* __restrict__ s, int batch, int cin, int cout, float scale2) {
+    const long long n = (long long)cout * cin;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
+        const int co = (int)(i / cin), ci = (int)(i - (long long)co * cin);
+        float a = 0.f;
+        for (int b = 0; b < batch; ++b) {
+            const float d = __ldg(demod + (size_t)b * cout + co);
+            const float q = -0.5f * d * d * d * scale2 * __ldg(g_demod + (size_t)b * cout + co);
+            const float v = __ldg(s + (size_t)b * cin + ci);
+            a = fmaf(q, v * v, a);
+        }
+        g_wsq[i] = a;
+    }
+}
+
+// g_s[b][ci] = 2 * s[b][ci] * sum_co q[b][co] * wsq[co][ci] + s_scale * g_sout[b][ci]
+// CTA = 32 consecutive ci x 8 warps striding over co; warp partials folded through shared memory in a fixed order.
+__global__ void __launch_bounds__(256)
+demod_bwd_s_kernel(float* __restrict__ g_s, const float* __restrict__ g_demod, const float* __restrict__ g_sout,
+                   const float* __restrict__ demod, const float* __restrict__ s, const float* __restrict__ wsq, int batch,
+                   int cin, int cout, float scale2, float s_scale) {
+    __shared__ float part[8][kDemodMaxBatch][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ci = blockIdx.x * 32 + lane;
+    float acc[kDemodMaxBatch];
+#pragma unroll
+    for (int b = 0; b < kDemodMaxBatch; ++b) acc[b] = 0.f;
+    if (ci < cin) {
+        for (int co = warp; co < cout; co += 8) {
+            const float w = __ldg(wsq + (size_t)co * cin + ci);
+#pragma unroll
+            for (int b = 0; b < kDemodMaxBatch; ++b)
+                if (b < batch) {
+                    const float d = __ldg(demod + (size_t)b * cout + co);
+                    const float q = -0.5f * d * d * d * scale2 * __ldg(g_demod + (size_t)b * cout + co);
+                    acc[b] = fmaf(q, w, acc[b]);
+                }
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < kDemodMaxBatch; ++b) part[warp][b][lane] = acc[b];
+    __syncthreads();
+    if (warp < batch && ci < cin) {                // warp b finishes sample b
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) a += part[w][warp][lane];
+        const size_t idx = (size_t)warp * cin + ci;
+        float r = 2.f * __ldg(s + idx) * a;
+        if (g_sout) r = fmaf(s_scale, __ldg(g_sout + idx), r);
+        g_s[idx] = r;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+add_scale_kernel(float4* __restrict__ out, const float4* __restrict__ a, const float4* __restrict__ b, float scale,
+                 long long n4) {
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += gridDim.x * 256LL) {
+        const float4 x = ld_stream_f4(a + i), y = ld_stream_f4(b + i);
+        st_stream_f4(out + i, make_float4((x.x + y.x) * scale, (x.y + y.y) * scale, (x.z + y.z) * scale, (x.w + y.w) * scale));
+    }
+}
+}  // namespace
+}  // namespace rick
+
+extern "C" int rick_demod_fwd(float* demod, float* s_out, const float* s, const float* wsq, int batch, int cin, int cout,
+                              float scale2, float eps, float s_scale, rick_stream_t stream) {
+    using namespace rick;
+    if (!demod || !s || !wsq || batch < 1 || cin < 1 || cout < 1) return RICK_ERR_INVALID_ARGUMENT;
+    if (batch > kDemodMaxBatch) return RICK_ERR_UNSUPPORTED;
+    const unsigned blocks = (unsigned)ceil_div((long long)cout * 32, 256);
+    demod_fwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(demod, s_out, s, wsq, batch, cin, cout, scale2,
+                                                                          eps, s_scale);
+    RICK_CHECK_LAUNCH();
+    return RICK_OK;
+}
+
+extern "C" int rick_demod_bwd(float* g_s, float* g_wsq, const float* g_demod, const float* g_sout, const float* demod,
+                              const float* s, const float* wsq, int batch, int cin, int cout, float scale2, float s_scale,
+                              rick_stream_t stream) {
+    using namespace rick;
+    if (!g_demod || !demod || !s || !wsq || batch < 1 || cin < 1 || cout < 1) return RICK_ERR_INVALID_ARGUMENT;
+    if (batch > kDemodMaxBatch) return RICK_ERR_UNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (g_wsq) {
+        long long blocks = ceil_div((long long)cout * cin, 256);
+        if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+        demod_bwd_wsq_kernel<<<(unsigned)blocks, 256, 0, st>>>(g_wsq, g_demod, demod, s, batch, cin, cout, scale2);
+        RICK_CHECK_LAUNCH();
+    }
+    if (g_s) {
+        demod_bwd_s_kernel<<<(unsigned)ceil_div(cin, 32), 256, 0, st>>>(g_s, g_demod, g_sout, demod, s, wsq, batch, cin, cout,
+                                                                        scale2, s_scale);
+        RICK_CHECK_LAUNCH();
+    }
+    return RICK_OK;
+}
+
+extern "C" int rick_add_scale(float* out, const float* a, const float* b, float scale, int64_t n, rick_stream_t stream) {
+    using namespace rick;
+    if (!out || !a || !b || n < 0) return RICK_ERR_INVALID_ARGUMENT;
+    if (n % 4 != 0) return RICK_ERR_UNSUPPORTED;
+    if (!aligned_to(out, 16) || !aligned_to(a, 16) || !aligned_to(b, 16)) return RICK_ERR_ALIGNMENT;
+    if (n == 0) return RICK_OK;
+    long long blocks = ceil_div(n / 4, 256);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    add_scale_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<float4*>(out), reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), scale, n / 4);
+    RICK_CHECK_LAUNCH();
+    return RICK_OK;
+}

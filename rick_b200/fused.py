@@ -27,6 +27,7 @@ from torch.nn import functional as F
 
 from . import conv_tc as ct
 from .op import upfirdn2d
+from .op import glue as _glue
 from .op.glue import weight_sqsum
 
 
@@ -110,8 +111,10 @@ class FusedGenerator:
             raw_conv = [p.mod(latent[:, i]) for p, i in zip(self.convs, conv_idx)]
             raw_rgb = [p.mod(latent[:, i]) for p, i in zip(self.rgbs, rgb_idx)]
         # conv(x * s, scale * W) == conv(x * (scale * s), W): the equalised-lr scale rides on the (B, Cin) style
-        s = [(r * p.wscale).contiguous() for p, r in zip(self.convs, raw_conv)]                       # (B, Cin)
-        demod = [torch.rsqrt(F.linear(si.pow(2), weight_sqsum(p.w)) + 1e-8).contiguous() for p, si in zip(self.convs, s)]
+        # (scaled style, demodulation) per layer: one launch each (rick_demod_fwd)
+        sd = [_glue.demod(r.contiguous(), weight_sqsum(p.w), p.wscale ** 2, 1e-8, p.wscale) for p, r in zip(self.convs, raw_conv)]
+        s = [x[1].contiguous() for x in sd]                                                           # (B, Cin)
+        demod = [x[0].contiguous() for x in sd]                                                       # (B, Cout)
         s_rgb = [r * p.wscale for p, r in zip(self.rgbs, raw_rgb)]
 
         def layer_noise(li, h, w):

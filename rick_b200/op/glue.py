@@ -223,3 +223,107 @@ def from_rgb(img, weight, bias, w_scale: float, negative_slope: float = 0.2, act
     """``fused_leaky_relu(conv2d(img, weight * w_scale), bias)`` for a 1x1 convolution from <= 4 channels; the result is a
     logical (B, Cout, H, W) tensor in channels-last memory."""
     return _FromRGB.apply(img, weight, bias, w_scale, negative_slope, act_scale)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# demodulation table of a ModulatedConv2d and the residual merge of a ResBlock
+# ---------------------------------------------------------------------------------------------------------------
+def _demod_composite(s, wsq, scale2: float, eps: float, s_scale: float):
+    """The same quantities as module code (model_probe_tune.py:246-251, algebraic form)."""
+    return torch.rsqrt(torch.nn.functional.linear(s.pow(2), wsq) * scale2 + eps), s * s_scale
+
+
+class _Demod(Function):
+    """(demod, s * s_scale) of one modulated convolution from its style ``s`` (B, Cin) and tap-summed squared weight
+    ``wsq`` (Cout, Cin): one launch forward, two for the first derivatives.  When the backward pass is itself being
+    differentiated (path-length regularisation, train:104-118) the gradient is re-derived with differentiable torch ops,
+    so higher derivatives are those of the module code."""
+
+    @staticmethod
+    def forward(ctx, s, wsq, scale2, eps, s_scale):
+        b, cin = s.shape
+        cout = wsq.shape[0]
+        demod = torch.empty(b, cout, dtype=torch.float32, device=s.device)
+        s_out = torch.empty_like(s)
+        with torch.cuda.device(s.device):
+            _lib.check(_lib.lib().rick_demod_fwd(demod.data_ptr(), s_out.data_ptr(), s.data_ptr(), wsq.data_ptr(), b, cin,
+                                                 cout, float(scale2), float(eps), float(s_scale), _stream()), "rick_demod_fwd")
+        ctx.save_for_backward(s, wsq, demod)
+        ctx.cfg = (float(scale2), float(eps), float(s_scale))
+        return demod, s_out
+
+    @staticmethod
+    def backward(ctx, g_demod, g_sout):
+        s, wsq, demod = ctx.saved_tensors
+        scale2, eps, s_scale = ctx.cfg
+        need_s, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if torch.is_grad_enabled():                      # double backward requested: differentiable composite
+            with torch.enable_grad():
+                s_ = s.detach().requires_grad_(True) if not s.requires_grad else s
+                w_ = wsq.detach().requires_grad_(True) if not wsq.requires_grad else wsq
+                d, so = _demod_composite(s_, w_, scale2, eps, s_scale)
+                outs, gouts = [], []
+                if g_demod is not None:
+                    outs.append(d), gouts.append(g_demod)
+                if g_sout is not None:
+                    outs.append(so), gouts.append(g_sout)
+                gs, gw = torch.autograd.grad(outs, (s_, w_), gouts, create_graph=True, allow_unused=True)
+            return (gs if need_s else None), (gw if need_w else None), None, None, None
+        b, cin = s.shape
+        cout = wsq.shape[0]
+        if g_demod is None:
+            return (g_sout * s_scale if need_s and g_sout is not None else None), None, None, None, None
+        g_demod = g_demod.contiguous()
+        g_sout = None if g_sout is None else g_sout.contiguous()
+        gs = torch.empty_like(s) if need_s else None
+        gw = torch.empty_like(wsq) if need_w else None
+        with torch.cuda.device(s.device):
+            _lib.check(_lib.lib().rick_demod_bwd(None if gs is None else gs.data_ptr(), None if gw is None else gw.data_ptr(),
+                                                 g_demod.data_ptr(), None if g_sout is None else g_sout.data_ptr(),
+                                                 demod.data_ptr(), s.data_ptr(), wsq.data_ptr(), b, cin, cout, scale2,
+                                                 s_scale, _stream()), "rick_demod_bwd")
+        return gs, gw, None, None, None
+
+
+import os as _os
+
+_FUSED_GLUE = _os.environ.get("RICK_FUSED_GLUE", "1") != "0"     # A/B switch for the demod / residual-merge kernels
+
+
+def demod_ok(s: torch.Tensor, wsq: torch.Tensor) -> bool:
+    return (_FUSED_GLUE and s.is_cuda and s.dtype == torch.float32 and s.dim() == 2 and s.shape[0] <= 8 and s.is_contiguous()
+            and wsq.dtype == torch.float32 and wsq.is_contiguous() and wsq.shape[1] == s.shape[1])
+
+
+def demod(s: torch.Tensor, wsq: torch.Tensor, scale2: float, eps: float, s_scale: float):
+    """(rsqrt(scale2 * s^2 @ wsq^T + eps), s * s_scale)."""
+    if demod_ok(s, wsq):
+        return _Demod.apply(s, wsq, scale2, eps, s_scale)
+    return _demod_composite(s, wsq, scale2, eps, s_scale)
+
+
+class _AddScale(Function):
+    @staticmethod
+    def forward(ctx, a, b, scale):
+        out = torch.empty_like(a)
+        with torch.cuda.device(a.device):
+            _lib.check(_lib.lib().rick_add_scale(out.data_ptr(), a.data_ptr(), b.data_ptr(), float(scale), a.numel(),
+                                                 _stream()), "rick_add_scale")
+        ctx.scale = float(scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        gs = g * ctx.scale                               # one pass, shared by both branches; differentiable again
+        return gs, gs, None
+
+
+def add_scale(a: torch.Tensor, b: torch.Tensor, scale: float) -> torch.Tensor:
+    """``(a + b) * scale`` (ResBlock's residual merge, model_probe_tune.py:655-660) as one pass when both operands are
+    dense float32 CUDA tensors with identical strides."""
+    if (_FUSED_GLUE and a.is_cuda and a.dtype == torch.float32 and b.dtype == torch.float32 and a.shape == b.shape
+            and a.stride() == b.stride() and a.numel() % 4 == 0 and a.numel() > 0
+            and (a.is_contiguous() or a.is_contiguous(memory_format=torch.channels_last))
+            and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0):
+        return _AddScale.apply(a, b, scale)
+    return (a + b) * scale

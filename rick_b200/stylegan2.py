@@ -266,8 +266,10 @@ class ModulatedConv2d(nn.Module):
         demod = None
         if self.demodulate:
             wsq = weight_sqsum(w)                                    # (Cout, Cin), one pass over the weight
-            demod = torch.rsqrt(F.linear(s.pow(2), wsq) * (self.scale ** 2) + self.eps)   # (B, Cout)
-        s = s * self.scale
+            # (B, Cout) demodulation and the scaled style in one launch (pow / mm / mul / add / rsqrt / mul as module code)
+            demod, s = _glue.demod(s.contiguous(), wsq, self.scale ** 2, self.eps, self.scale)
+        else:
+            s = s * self.scale
         return _conv.modulated_conv2d(input, w, s, demod, upsample=self.upsample, downsample=self.downsample,
                                       padding=self.padding, blur=getattr(self, "blur", None), epilogue=epilogue)
 
@@ -524,7 +526,7 @@ class ResBlock(nn.Module):
         h2 = self.conv2(h1)
         if feats is not None:
             feats += [h1, h2]
-        return (h2 + self.skip(input)) / math.sqrt(2)
+        return _glue.add_scale(h2, self.skip(input), 1 / math.sqrt(2))
 
 
 class Discriminator(nn.Module):

@@ -511,3 +511,52 @@ def test_from_rgb_fused_layer_matches_modules_to_second_order():
             torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5, msg=name)
     finally:
         torch.backends.cudnn.allow_tf32 = prev
+
+
+@pytest.mark.parametrize("shape", [(2, 512, 512), (1, 128, 256), (4, 256, 128), (8, 64, 32)], ids=str)
+def test_demod_fused_matches_module_code_to_second_order(shape):
+    """rick_demod_fwd / rick_demod_bwd against the module code they replace (model_probe_tune.py:246-251 in algebraic form:
+    pow / linear / mul / add / rsqrt), first derivatives from the fused backward, second derivatives through the
+    differentiable composite branch (what the path-length regulariser differentiates)."""
+    from rick_b200.op import glue
+    b, cin, cout = shape
+    g = torch.Generator(device="cuda").manual_seed(cin + cout)
+    s0 = torch.randn(b, cin, device="cuda", generator=g) * 0.5 + 1.0
+    w0 = torch.rand(cout, cin, device="cuda", generator=g) * 9.0
+    scale2, eps, s_scale = 1.0 / (cin * 9), 1e-8, (cin * 9) ** -0.5
+    gd = torch.randn(b, cout, device="cuda", generator=g)
+    gs = torch.randn(b, cin, device="cuda", generator=g)
+
+    def run(fn, second):
+        s, w = s0.clone().requires_grad_(True), w0.clone().requires_grad_(True)
+        d, so = fn(s, w, scale2, eps, s_scale)
+        g_s, g_w = torch.autograd.grad((d, so), (s, w), (gd, gs), create_graph=second)
+        if not second:
+            return d, so, g_s, g_w
+        gg_s, gg_w = torch.autograd.grad((g_s * gs).sum() + (g_w.square()).sum(), (s, w))
+        return d, so, g_s, g_w, gg_s, gg_w
+
+    for second in (False, True):
+        got = run(glue.demod, second)
+        want = run(glue._demod_composite, second)
+        for a, e in zip(got, want):
+            assert (a - e).abs().max().item() <= 2e-5 * max(e.abs().max().item(), 1e-6)
+
+
+def test_add_scale_matches_residual_merge():
+    """rick_add_scale = ResBlock's (out + skip) / sqrt(2) (model_probe_tune.py:655-660), NCHW and channels-last, with its
+    gradient; odd element counts fall back to the torch expression."""
+    from rick_b200.op import glue
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for shape, cl in (((4, 256, 32, 32), True), ((2, 512, 8, 8), False), ((1, 3, 5, 5), False)):
+        a = torch.randn(*shape, device="cuda", generator=g)
+        b = torch.randn(*shape, device="cuda", generator=g)
+        if cl:
+            a, b = a.contiguous(memory_format=torch.channels_last), b.contiguous(memory_format=torch.channels_last)
+        a.requires_grad_(True), b.requires_grad_(True)
+        out = glue.add_scale(a, b, 2 ** -0.5)
+        want = (a.detach() + b.detach()) * 2 ** -0.5
+        assert out.stride() == want.stride() and torch.equal(out, want)
+        go = torch.randn_like(out)
+        ga, gb = torch.autograd.grad(out, (a, b), go)
+        assert torch.equal(ga, go * 2 ** -0.5) and torch.equal(gb, ga)
