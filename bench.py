@@ -542,7 +542,8 @@ def conv_step_profile(device, tf32_peak, ms_per_step, with_cudnn=True):
     from rick_b200 import conv
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
     cl = lambda t: t.contiguous(memory_format=torch.channels_last)
-    agg = {"fprop": [0.0, 0.0, 0.0, 0], "dgrad": [0.0, 0.0, 0.0, 0], "wgrad": [0.0, 0.0, 0.0, 0]}   # flops, us tc, us cudnn, n
+    agg = {"fprop": [0.0, 0.0, 0.0, 0, 0.0], "dgrad": [0.0, 0.0, 0.0, 0, 0.0],
+           "wgrad": [0.0, 0.0, 0.0, 0, 0.0]}                   # flops, us tc, us cudnn, launches, algorithmic DRAM bytes
     table = []
     prev_tf32 = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = True
@@ -568,6 +569,7 @@ def conv_step_profile(device, tf32_peak, ms_per_step, with_cudnn=True):
                 n = prims.count(prim)
                 a = agg[prim]
                 a[0] += flops * n
+                a[4] += 4.0 * (x.numel() + y.numel() + wt.numel()) * n     # each operand read / result written once
                 a[1] += us * n
                 a[2] += (us_lib or 0.0) * n
                 a[3] += n
@@ -587,6 +589,8 @@ def conv_step_profile(device, tf32_peak, ms_per_step, with_cudnn=True):
                 "frac": ach / tf32_peak, "traffic": _traffic(kernel),
                 "peak_source": "measured in this run: torch.matmul TF32 8192^3, best of 10 (MEASURED_PEAKS.json has "
                                "bf16 only: bf16_tflops / 2 = %.1f)" % (load_peaks()["bf16_tflops"] / 2),
+                "traffic_note": "summed DRAM bytes of this kernel's launches in one iteration (profiles/r02*_conv_traffic.md)",
+                "algorithmic_bytes_per_iteration": sum(agg[p][4] for p in prims),
                 "launches_per_iteration": sum(agg[p][3] for p in prims), "sum_launch_us": us,
                 "share_of_step": us * 1e-3 / ms_per_step, "algorithmic_flops_per_iteration": fl,
                 "cudnn_tf32_same_launches_us": us_lib if with_cudnn else None, "note": note}

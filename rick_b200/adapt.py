@@ -21,6 +21,7 @@ All randomness comes from a ``DrawStream`` so that a seeded CPU oracle run can c
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
@@ -161,7 +162,9 @@ class RickAdapter:
         # gradients land together when backward ends): last bucket.  D's equalised-lr scaling runs as one node per
         # bucket, so that a bucket's gradients reach the leaves -- and its all-reduce starts -- while backward goes on.
         g_late = [p for n, p in self.g_named.items() if "convs" in n and "modulation" in n]
-        self._gsync = {"g": rdist.GradSync(self.g_train, late=g_late), "d": rdist.GradSync(self.d_train)}
+        nbk = int(os.environ.get("RICK_DDP_BUCKETS", "4"))
+        self._gsync = {"g": rdist.GradSync(self.g_train, n_buckets=nbk, late=g_late),
+                       "d": rdist.GradSync(self.d_train, n_buckets=nbk)}
         if self.device.type == "cuda":
             from . import stylegan2 as _sg
             _sg.declare_prescale_groups(generator, self.g_train)          # trainable subset | rest

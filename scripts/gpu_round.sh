@@ -25,6 +25,13 @@ ncu)
       python -u bench.py --steps 1 --warmup 3 --no-cpu-baseline --quick --cuda-profiler ${NCU_BENCH_ARGS:---mode eager} \
       > gpurun_out/ncu_bench${NCU_TAG}.log 2>&1
   echo "ncu launches rc=$?" ;;
+ncutraffic)
+  # DRAM bytes of every conv_tc / conv_wgrad launch of ONE timed iteration (one metric pass): roofline.traffic
+  timeout 400 ncu --profile-from-start off --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum \
+      --clock-control none -k regex:'conv_tc_kernel|conv_wgrad_kernel' -c 400 --csv --log-file gpurun_out/conv_traffic${NCU_TAG}.csv \
+      python -u bench.py --steps 1 --warmup 3 --no-cpu-baseline --quick --cuda-profiler --mode eager \
+      > gpurun_out/ncu_traffic${NCU_TAG}.log 2>&1
+  echo "ncu traffic rc=$?" ;;
 ncuops)
   timeout 300 ncu --set full --clock-control none --import-source on \
       -k regex:${NCU_KERNELS:-'upfirdn2d|bias_act_vec|bias_act_bwd|blur_nhwc|conv_tc|conv_wgrad|adam_mask_ema'} -s ${NCU_SKIP:-9} -c ${NCU_COUNT:-9} \
