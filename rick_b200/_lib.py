@@ -11,7 +11,7 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_ulonglong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librick_b200.so")
+LIB_PATH = os.environ.get("RICK_B200_LIB") or os.path.join(_HERE, "librick_b200.so")   # (override: A/B of builds)
 
 RICK_F32, RICK_BF16 = 0, 1
 ACT_LINEAR, ACT_LRELU = 1, 3
