@@ -397,27 +397,36 @@ demod_bwd_wsq_kernel(float* __restrict__ g_wsq, const float* __restrict__ g_demo
 }
 
 // g_s[b][ci] = 2 * s[b][ci] * sum_co q[b][co] * wsq[co][ci] + s_scale * g_sout[b][ci]
-// CTA = 32 consecutive ci x 8 warps striding over co; warp partials folded through shared memory in a fixed order.
+// CTA = 32 consecutive ci x 8 warps striding over co.  q is staged in shared memory once; every warp keeps 8 rows of wsq
+// in flight (the first version walked co one dependent load at a time: 36 us per layer, more than the convolution it
+// serves at 4 .. 16 px).  Warp partials are folded through shared memory in a fixed order.
 __global__ void __launch_bounds__(256)
 demod_bwd_s_kernel(float* __restrict__ g_s, const float* __restrict__ g_demod, const float* __restrict__ g_sout,
                    const float* __restrict__ demod, const float* __restrict__ s, const float* __restrict__ wsq, int batch,
                    int cin, int cout, float scale2, float s_scale) {
+    extern __shared__ float s_q[];                         // [batch][cout]
     __shared__ float part[8][kDemodMaxBatch][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < batch * cout; i += 256) {
+        const float d = __ldg(demod + i);
+        s_q[i] = -0.5f * d * d * d * scale2 * __ldg(g_demod + i);
+    }
+    __syncthreads();
     const int ci = blockIdx.x * 32 + lane;
     float acc[kDemodMaxBatch];
 #pragma unroll
     for (int b = 0; b < kDemodMaxBatch; ++b) acc[b] = 0.f;
-    if (ci < cin) {
-        for (int co = warp; co < cout; co += 8) {
-            const float w = __ldg(wsq + (size_t)co * cin + ci);
+    for (int co0 = warp * 8; co0 < cout; co0 += 64) {
+        float w[8];
 #pragma unroll
-            for (int b = 0; b < kDemodMaxBatch; ++b)
-                if (b < batch) {
-                    const float d = __ldg(demod + (size_t)b * cout + co);
-                    const float q = -0.5f * d * d * d * scale2 * __ldg(g_demod + (size_t)b * cout + co);
-                    acc[b] = fmaf(q, w, acc[b]);
-                }
+        for (int j = 0; j < 8; ++j) w[j] = (ci < cin && co0 + j < cout) ? __ldg(wsq + (size_t)(co0 + j) * cin + ci) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (co0 + j < cout) {
+#pragma unroll
+                for (int b = 0; b < kDemodMaxBatch; ++b)
+                    if (b < batch) acc[b] = fmaf(s_q[b * cout + co0 + j], w[j], acc[b]);
+            }
         }
     }
 #pragma unroll
@@ -471,8 +480,9 @@ extern "C" int rick_demod_bwd(float* g_s, float* g_wsq, const float* g_demod, co
         RICK_CHECK_LAUNCH();
     }
     if (g_s) {
-        demod_bwd_s_kernel<<<(unsigned)ceil_div(cin, 32), 256, 0, st>>>(g_s, g_demod, g_sout, demod, s, wsq, batch, cin, cout,
-                                                                        scale2, s_scale);
+        if ((size_t)batch * cout * sizeof(float) > 40 * 1024) return RICK_ERR_UNSUPPORTED;
+        demod_bwd_s_kernel<<<(unsigned)ceil_div(cin, 32), 256, (size_t)batch * cout * sizeof(float), st>>>(
+            g_s, g_demod, g_sout, demod, s, wsq, batch, cin, cout, scale2, s_scale);
         RICK_CHECK_LAUNCH();
     }
     return RICK_OK;

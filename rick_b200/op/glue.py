@@ -292,7 +292,8 @@ _FUSED_GLUE = _os.environ.get("RICK_FUSED_GLUE", "1") != "0"     # A/B switch fo
 
 def demod_ok(s: torch.Tensor, wsq: torch.Tensor) -> bool:
     return (_FUSED_GLUE and s.is_cuda and s.dtype == torch.float32 and s.dim() == 2 and s.shape[0] <= 8 and s.is_contiguous()
-            and wsq.dtype == torch.float32 and wsq.is_contiguous() and wsq.shape[1] == s.shape[1])
+            and wsq.dtype == torch.float32 and wsq.is_contiguous() and wsq.shape[1] == s.shape[1]
+            and s.shape[0] * wsq.shape[0] * 4 <= 40 * 1024)
 
 
 def demod(s: torch.Tensor, wsq: torch.Tensor, scale2: float, eps: float, s_scale: float):

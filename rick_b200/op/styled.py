@@ -8,8 +8,8 @@ i.e. ModulatedConv2d's modulation / demodulation in the algebraic form (model_pr
 plus all broadcast-gradient reductions), instead of the ~10 broadcast / reduce kernels per layer autograd would launch.
 
 Second derivatives (path-length regularisation differentiates through G twice): when ``backward`` runs with grad mode
-enabled (``create_graph=True``) it evaluates the same formulas with differentiable torch ops on the saved tensors, so
-autograd can differentiate them again; the fused kernels serve the ordinary first-order backward.
+enabled (``create_graph=True``) it is itself a differentiable fused op (``_ModulateBwd``, the bias-act backward Function)
+whose derivatives are again these kernels, so autograd can differentiate to any order without leaving them.
 """
 from __future__ import annotations
 
@@ -36,6 +36,47 @@ def _ws(b, hw, c, device):
     return torch.empty(n, dtype=torch.uint8, device=device)
 
 
+def _modulate_bwd_launch(gy, x, s):
+    b, c, h, w = x.shape
+    gx = torch.empty_like(x, memory_format=torch.channels_last)
+    gs = torch.empty(b, c, dtype=torch.float32, device=x.device)
+    ws = _ws(b, h * w, c, x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().rick_modulate_bwd_nhwc(gx.data_ptr(), gs.data_ptr(), ws.data_ptr(), gy.data_ptr(),
+                                                     x.data_ptr(), s.data_ptr(), b, h * w, c, _stream()),
+                   "rick_modulate_bwd_nhwc")
+    return gx, gs
+
+
+class _ModulateBwd(Function):
+    """(gy * s[b, c], sum_hw gy * x) -- the backward of ``modulate`` -- as a differentiable op of its own, ONE launch.
+    Its derivatives are again modulate / modulate-backward calls, so the path-length regulariser's second backward runs on
+    the fused kernels to any order (round 2: the composite torch formulas it replaces were 2.6 ms of the 11 ms path-length
+    sub-step -- spatial sums of channels-last tensors are ATen's slow case, 78 us for a 33 MB tensor)."""
+
+    @staticmethod
+    def forward(ctx, gy, x, s):
+        ctx.save_for_backward(gy, x, s)
+        return _modulate_bwd_launch(gy, x, s)
+
+    @staticmethod
+    def backward(ctx, ggx, ggs):
+        gy, x, s = ctx.saved_tensors
+        need_gy, need_x, need_s = ctx.needs_input_grad
+        d_gy = d_x = d_s = None
+        if ggx is not None and (need_gy or need_s):
+            t1, d_s = _ModulateBwd.apply(_cl(ggx), gy, s)          # ggx * s and sum_hw ggx * gy in one launch
+            d_gy = t1
+        if ggs is not None:
+            ggs = ggs.contiguous()
+            if need_gy:
+                t2 = _Modulate.apply(x, ggs)
+                d_gy = t2 if d_gy is None else d_gy + t2
+            if need_x:
+                d_x = _Modulate.apply(gy, ggs)
+        return (d_gy if need_gy else None), d_x, (d_s if need_s else None)
+
+
 class _Modulate(Function):
     @staticmethod
     def forward(ctx, x, s):
@@ -52,18 +93,9 @@ class _Modulate(Function):
     @staticmethod
     def backward(ctx, gy):
         x, s = ctx.saved_tensors
-        if torch.is_grad_enabled():                       # double backward requested: differentiable composite
-            return gy * s[:, :, None, None], (gy * x).sum((2, 3))
-        gy = _cl(gy)
-        b, c, h, w = x.shape
-        gx = torch.empty_like(x, memory_format=torch.channels_last)
-        gs = torch.empty(b, c, dtype=torch.float32, device=x.device)
-        ws = _ws(b, h * w, c, x.device)
-        with torch.cuda.device(x.device):
-            _lib.check(_lib.lib().rick_modulate_bwd_nhwc(gx.data_ptr(), gs.data_ptr(), ws.data_ptr(), gy.data_ptr(),
-                                                         x.data_ptr(), s.data_ptr(), b, h * w, c, _stream()),
-                       "rick_modulate_bwd_nhwc")
-        return gx, gs
+        if torch.is_grad_enabled():                       # double backward requested: the differentiable fused op
+            return _ModulateBwd.apply(_cl(gy), x, s)
+        return _modulate_bwd_launch(_cl(gy), x, s)
 
 
 class _StyledEpilogue(Function):
@@ -85,11 +117,15 @@ class _StyledEpilogue(Function):
     def backward(ctx, gy):
         a, demod, noise, noise_weight, y = ctx.saved_tensors
         b, c, h, w = a.shape
-        if torch.is_grad_enabled():                       # double backward requested: differentiable composite
-            t = torch.where(y > 0, gy, gy * ctx.alpha) * ctx.scale
-            nz = noise.view(b, 1, h, w)
-            return (t * demod[:, :, None, None], (t * a).sum((2, 3)), None, (t * nz).sum().reshape(1), t.sum((0, 2, 3)),
-                    None, None)
+        if torch.is_grad_enabled():
+            # double backward requested: the same quantities from two differentiable fused ops -- the activation gradient
+            # (t, sum t) from the bias-act backward (op/fused_act.py:19-48) and (t * demod, sum_hw t * a) from the
+            # modulate backward; only the scalar noise-weight gradient stays a torch expression
+            from .fused_act import FusedLeakyReLUFunctionBackward
+            t, gb = FusedLeakyReLUFunctionBackward.apply(_cl(gy), y, ctx.alpha, ctx.scale)
+            ga, gd = _ModulateBwd.apply(t, a, demod)
+            gnw = (t.sum(1).reshape(b, h * w) * noise).sum().reshape(1)
+            return ga, gd, None, gnw, gb, None, None
         gy = _cl(gy)
         ga = torch.empty_like(a, memory_format=torch.channels_last)
         gd = torch.empty(b, c, dtype=torch.float32, device=a.device)
