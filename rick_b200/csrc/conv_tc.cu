@@ -446,36 +446,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     }
 }
 
-// Split-K fold: out = epilogue( sum_s ws[s] ), the partial planes added in index order (deterministic).  One thread owns
-// 4 consecutive channels of one output pixel (NHWC).  The TF32 truncation compensation was applied to the partials.
+// Split-K fold: out = epilogue( sum_s ws[s] ).  A group of sg = 2^k >= splits lanes owns 4 consecutive channels of one
+// output pixel (NHWC): lane j loads the quad of partial plane j -- all planes in flight at once, one L2 round trip instead
+// of splits / 4 -- and the group adds them with a fixed xor-shuffle tree (deterministic); its first lane applies the
+// epilogue and stores.  The TF32 truncation compensation was applied to the partials.
 template <bool ACT>
 __global__ void __launch_bounds__(256)
-conv_fold_kernel(float* __restrict__ out, float* __restrict__ out2, const float* __restrict__ ws, int splits,
+conv_fold_kernel(float* __restrict__ out, float* __restrict__ out2, const float* __restrict__ ws, int splits, int sg_log2,
                  long long plane, int cout, int hw, const float* __restrict__ demod, const float* __restrict__ noise,
                  const float* __restrict__ noise_w, const float* __restrict__ bias, const float* __restrict__ s_next,
                  float alpha, float scale) {
     const long long quads = plane / 4;
     const int cq = cout / 4;
     const float nw = noise ? __ldg(noise_w) : 0.f;
-    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < quads;
-         q += (long long)gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const int sl = lane & ((1 << sg_log2) - 1);                 // which partial plane this lane loads
+    const int per_warp = 32 >> sg_log2;                          // quads per warp
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long qw = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * per_warp; qw < quads;
+         qw += warps * per_warp) {
+        const long long q = qw + (lane >> sg_log2);
+        const bool valid = q < quads;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid && sl < splits) a = ld_stream_f4(reinterpret_cast<const float4*>(ws + (long long)sl * plane) + q);
+        for (int o = (1 << sg_log2) >> 1; o > 0; o >>= 1) {
+            a.x += __shfl_xor_sync(0xffffffffu, a.x, o), a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+            a.z += __shfl_xor_sync(0xffffffffu, a.z, o), a.w += __shfl_xor_sync(0xffffffffu, a.w, o);
+        }
+        if (!valid || sl != 0) continue;
         const long long pix = q / cq;
         const int co = (int)(q - pix * cq) * 4;
         const int b = (int)(pix / hw);
-        float4 a = ld_stream_f4(reinterpret_cast<const float4*>(ws) + q);
-        int s = 1;
-        for (; s + 4 <= splits; s += 4) {        // four loads in flight (a 32-way split is otherwise 32 serial L2 trips)
-            const float4 v0 = ld_stream_f4(reinterpret_cast<const float4*>(ws + (s + 0) * plane) + q);
-            const float4 v1 = ld_stream_f4(reinterpret_cast<const float4*>(ws + (s + 1) * plane) + q);
-            const float4 v2 = ld_stream_f4(reinterpret_cast<const float4*>(ws + (s + 2) * plane) + q);
-            const float4 v3 = ld_stream_f4(reinterpret_cast<const float4*>(ws + (s + 3) * plane) + q);
-            a.x = (((a.x + v0.x) + v1.x) + v2.x) + v3.x, a.y = (((a.y + v0.y) + v1.y) + v2.y) + v3.y;
-            a.z = (((a.z + v0.z) + v1.z) + v2.z) + v3.z, a.w = (((a.w + v0.w) + v1.w) + v2.w) + v3.w;
-        }
-        for (; s < splits; ++s) {
-            const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(ws + s * plane) + q);
-            a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
-        }
         if (demod) {
             const float4 d = __ldg(reinterpret_cast<const float4*>(demod + (size_t)b * cout + co));
             a.x *= d.x, a.y *= d.y, a.z *= d.z, a.w *= d.w;
@@ -692,19 +693,21 @@ extern "C" int rick_conv_tc_w(void* out, const void* xm, const rick_conv_weight*
     kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmap_w, tmap_x[0], tmap_x[1], tmap_x[2], tmap_x[3], p);
     RICK_CHECK_LAUNCH();
     if (ksplit > 1) {
-        long long blocks = ceil_div(out_elems / 4, 256);
-        if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+        int sg_log2 = 1;
+        while ((1 << sg_log2) < ksplit) ++sg_log2;              // ksplit <= 32
+        long long blocks = ceil_div((out_elems / 4) << sg_log2, 256);
+        if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
         const float* ws = static_cast<const float*>(workspace);
         const int hw = g->out_h * g->out_w;
         float* o = static_cast<float*>(out);
         cudaStream_t st = static_cast<cudaStream_t>(stream);
         if (e && e->act)
-            conv_fold_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(o, static_cast<float*>(e->out2), ws, ksplit, out_elems,
-                                                                      g->cout, hw, e->demod, e->noise, e->noise_weight,
-                                                                      e->bias, e->s_next, e->alpha, e->scale);
+            conv_fold_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(o, static_cast<float*>(e->out2), ws, ksplit, sg_log2,
+                                                                      out_elems, g->cout, hw, e->demod, e->noise,
+                                                                      e->noise_weight, e->bias, e->s_next, e->alpha, e->scale);
         else
             conv_fold_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(o, e ? static_cast<float*>(e->out2) : nullptr, ws, ksplit,
-                                                                       out_elems, g->cout, hw, e ? e->demod : nullptr,
+                                                                       sg_log2, out_elems, g->cout, hw, e ? e->demod : nullptr,
                                                                        e ? e->noise : nullptr, e ? e->noise_weight : nullptr,
                                                                        e ? e->bias : nullptr, e ? e->s_next : nullptr, 0.f, 1.f);
         RICK_CHECK_LAUNCH();
