@@ -225,7 +225,11 @@ class RickAdapter:
         fake_pred, real_pred = d_pair(self.d_ema, fake, real)
         g_loss = g_nonsaturating_loss(fake_pred)
         d_loss = d_logistic_loss(real_pred, fake_pred)
-        g_grads = autograd.grad(g_loss, list(self.g_ema.parameters()), retain_graph=True)
+        # the generator loss reaches G's parameters THROUGH D: D's own weight gradients are not part of this pass
+        from . import conv as _conv
+        d_ptrs = set(getattr(self.d_ema, "_scaled_weight_ptrs", ())) | {p.data_ptr() for p in self.d_ema.parameters()}
+        with _conv.skip_weight_grads(d_ptrs):
+            g_grads = autograd.grad(g_loss, list(self.g_ema.parameters()), retain_graph=True)
         d_grads = autograd.grad(d_loss, list(self.d_ema.parameters()))
         self.acc_g.add(g_grads, first=False)
         self.acc_d.add(d_grads, first=False)

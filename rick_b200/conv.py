@@ -32,6 +32,32 @@ from .op import styled as _styled
 _FORCE = os.environ.get("RICK_CONV_BACKEND", "")   # "", "cudnn" or "tc" (tests use it to pin an executor)
 launch_stats = {"tc": 0, "library": 0}
 
+# Weight tensors (by data pointer) whose gradient the backward pass in flight does not want.  ``ctx.needs_input_grad`` is fixed
+# when the forward runs, so a backward restricted to OTHER tensors (the Fisher round differentiates the generator loss through
+# D for G's parameters only, train:239-247) would still compute -- and autograd then drop -- every weight gradient of D.
+_NO_WGRAD_PTRS: set = set()
+
+
+class skip_weight_grads:
+    """``with skip_weight_grads(ptrs):`` -- the convolution Functions skip the weight gradients of these weights."""
+
+    def __init__(self, ptrs):
+        self.ptrs = set(ptrs)
+
+    def __enter__(self):
+        self.prev = set(_NO_WGRAD_PTRS)
+        _NO_WGRAD_PTRS.update(self.ptrs)
+        return self
+
+    def __exit__(self, *exc):
+        _NO_WGRAD_PTRS.clear()
+        _NO_WGRAD_PTRS.update(self.prev)
+        return False
+
+
+def _wants_wgrad(w: torch.Tensor) -> bool:
+    return not _NO_WGRAD_PTRS or w.data_ptr() not in _NO_WGRAD_PTRS
+
 
 # ---------------------------------------------------------------------------------------------------------------
 # primitives
@@ -152,7 +178,7 @@ class _Conv(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         x, w = ctx.saved_tensors
-        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and _wants_wgrad(w)
         if not torch.is_grad_enabled():                    # plain backward (no create_graph): straight to the kernels
             gx = _dgrad(g, w, x, ctx.cfg) if need_x else None
             gw = _wgrad(g, x, w, ctx.cfg) if need_w else None
@@ -213,6 +239,7 @@ class _ConvBiasAct(torch.autograd.Function):
         from .op.fused_act import FusedLeakyReLUFunctionBackward
         x, w, out = ctx.saved_tensors
         need_x, need_w, need_b = ctx.needs_input_grad[:3]
+        need_w = need_w and _wants_wgrad(w)
         g_pre, g_bias = FusedLeakyReLUFunctionBackward.apply(g, out, *ctx.act)
         gx = gw = None
         if need_x or need_w:

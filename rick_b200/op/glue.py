@@ -192,6 +192,9 @@ class _FromRGB(Function):
         img, weight, y = ctx.saved_tensors
         w_scale, alpha, act_scale, has_bias = ctx.cfg
         need_img, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2] and has_bias
+        from .. import conv as _conv
+        if not _conv._wants_wgrad(weight):                 # a backward restricted to other tensors (Fisher round, G's loss)
+            need_w = need_b = False
         b, cin, h, w = img.shape
         cout = weight.shape[0]
         w2 = weight.reshape(cout, cin)

@@ -157,6 +157,8 @@ class _Prescaled:
 
     def __init__(self, net: nn.Module):
         self.groups = getattr(net, "_prescale_groups", None) if _PRESCALE else None
+        self.ptrs = set()                                  # data pointers of the scaled weights of this pass
+        object.__setattr__(net, "_scaled_weight_ptrs", self.ptrs)
 
     def __enter__(self):
         if self.groups and self.groups[0][0][2].is_cuda:
@@ -164,6 +166,7 @@ class _Prescaled:
                 outs = scale_all([p for _, _, p, _ in grp], [s for *_, s in grp])
                 for (m, slot, _, _), o in zip(grp, outs):
                     setattr(m, slot, o)
+                    self.ptrs.add(o.data_ptr())
         return self
 
     def __exit__(self, *exc):
