@@ -235,6 +235,11 @@ typedef struct rick_conv_weight {
 } rick_conv_weight;
 
 RICK_API int64_t rick_conv_tc_workspace(const rick_conv_geom* geom);
+/* The launch plan rick_conv_tc_w would use for `geom` (host only, no device work): per phase the pixel tile
+ * tile_w[i] x tile_h[i] (arrays of 4), the samples per tile, the K ranges per tile (1 = no split) and the number of output
+ * tiles.  Tiles hold at most 256 pixels; single-phase launches are planned by waves over the SMs. */
+RICK_API int rick_conv_tc_plan(const rick_conv_geom* geom, int* tile_w, int* tile_h, int* samples_per_tile, int* ksplit,
+                               int* total_tiles);
 RICK_API int rick_conv_tc_w(void* out, const void* xm, const rick_conv_weight* weight, const rick_conv_geom* geom,
                             const rick_conv_epilogue* epilogue, void* workspace, int64_t workspace_bytes,
                             rick_stream_t stream);

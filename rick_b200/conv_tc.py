@@ -45,6 +45,17 @@ _lib._OPTIONAL["rick_conv_tc"] = (c_int, [c_void_p, c_void_p, c_void_p, ctypes.P
 _lib._OPTIONAL["rick_conv_tc_w"] = (c_int, [c_void_p, c_void_p, ctypes.POINTER(ConvWeight), ctypes.POINTER(ConvGeom),
                                             ctypes.POINTER(ConvEpilogue), c_void_p, c_int64, c_void_p])
 _lib._OPTIONAL["rick_conv_tc_workspace"] = (c_int64, [ctypes.POINTER(ConvGeom)])
+_lib._OPTIONAL["rick_conv_tc_plan"] = (ctypes.c_int, [ctypes.POINTER(ConvGeom)] + [ctypes.POINTER(ctypes.c_int)] * 5)
+
+
+def launch_plan(geom: "ConvGeom") -> dict:
+    """The tile plan ``rick_conv_tc_w`` would use (host logic only; works without a GPU)."""
+    tw, th = (ctypes.c_int * 4)(), (ctypes.c_int * 4)()
+    nb, ks, tot = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    _lib.check(_lib.lib().rick_conv_tc_plan(ctypes.byref(geom), tw, th, ctypes.byref(nb), ctypes.byref(ks), ctypes.byref(tot)),
+               "rick_conv_tc_plan")
+    return {"tiles": [(tw[i], th[i]) for i in range(geom.n_phases)], "samples_per_tile": nb.value, "ksplit": ks.value,
+            "total_tiles": tot.value}
 _lib._OPTIONAL["rick_conv_wgrad_workspace"] = (c_int64, [ctypes.POINTER(WgradGeom)])
 _lib._OPTIONAL["rick_conv_wgrad_tc"] = (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                                                 ctypes.POINTER(WgradGeom), c_void_p, c_float, c_void_p])

@@ -553,6 +553,20 @@ extern "C" int64_t rick_conv_tc_workspace(const rick_conv_geom* g) {
     return (int64_t)tp.ksplit * g->batch * g->out_h * g->out_w * g->cout * 4;
 }
 
+extern "C" int rick_conv_tc_plan(const rick_conv_geom* g, int* tile_w, int* tile_h, int* samples_per_tile, int* ksplit,
+                                 int* total_tiles) {
+    using namespace rick;
+    if (!g || !tile_w || !tile_h || !samples_per_tile || !ksplit || !total_tiles) return RICK_ERR_INVALID_ARGUMENT;
+    if (g->n_phases < 1 || g->n_phases > 4) return RICK_ERR_INVALID_ARGUMENT;
+    if (g->cout % 32 != 0 || g->cin % kBlockK != 0) return RICK_ERR_UNSUPPORTED;
+    TilePlan tp;
+    const int rc = plan_tiles(g, tp);
+    if (rc != RICK_OK) return rc;
+    for (int i = 0; i < 4; ++i) tile_w[i] = i < g->n_phases ? tp.ptw[i] : 0, tile_h[i] = i < g->n_phases ? tp.pth[i] : 0;
+    *samples_per_tile = tp.nb, *ksplit = tp.ksplit, *total_tiles = tp.total_tiles;
+    return RICK_OK;
+}
+
 extern "C" int rick_conv_tc_w(void* out, const void* xm, const rick_conv_weight* wd, const rick_conv_geom* g,
                               const rick_conv_epilogue* e, void* workspace, int64_t workspace_bytes,
                               rick_stream_t stream) {

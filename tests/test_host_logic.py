@@ -484,3 +484,31 @@ def test_transposed_conv_geometries_match_torch():
     torch.testing.assert_close(got, nhwc(gx))
     got = _interp_wgrad(nhwc(go), nhwc(x), ct.geom_wgrad(B, h, w, cin, cout, k, 2, 0, transposed=True), k)
     torch.testing.assert_close(got, gw)
+
+
+def test_conv_tile_planner_host_logic():
+    """rick_conv_tc_plan (host only, runs without a GPU): tiles hold <= 256 pixels and cover the map; single-phase launches
+    are planned by waves over the 148 SMs (512 tiles of 256 pixels would leave the 4th round half empty: 592 tiles of 224);
+    maps with fewer tiles than SMs get a split-K plan; several samples share a tile on tiny maps."""
+    from rick_b200 import conv_tc as ct
+
+    def plan(b, h, cin, cout, k=3, stride=1, pad=1):
+        g = ct.geom_conv(b, h, h, cin, cout, k, stride, pad)
+        p = ct.launch_plan(g)
+        for (tw, th), ph in zip(p["tiles"], [g.phase[i] for i in range(g.n_phases)]):
+            assert 1 <= tw <= ph.cols and 1 <= th <= ph.rows and tw * th * p["samples_per_tile"] <= 256
+        return p
+
+    p = plan(2, 256, 128, 128)                      # G's 256 px layer at batch 2
+    assert p["ksplit"] == 1 and p["samples_per_tile"] == 1
+    tw, th = p["tiles"][0]
+    tiles = -(-256 // tw) * -(-256 // th) * 2
+    assert tiles == p["total_tiles"] and tiles % 148 == 0 and tw * th < 256, p      # whole waves of smaller tiles
+    p4 = plan(4, 256, 128, 128)                     # 1024 tiles of 256 pixels: 6.9 rounds, nothing to gain
+    assert p4["tiles"][0][0] * p4["tiles"][0][1] == 256 and p4["total_tiles"] == 1024
+    small = plan(2, 8, 512, 512)                    # 2 x 64 pixels: one pixel tile, 4 cout tiles -> split K
+    assert small["samples_per_tile"] == 2 and small["total_tiles"] == 4 and small["ksplit"] > 1
+    big = plan(64, 64, 512, 512)                    # sample generation: plenty of tiles, no split
+    assert big["ksplit"] == 1 and big["total_tiles"] == 64 * 16 * 4
+    up = ct.launch_plan(ct.geom_conv_transpose_s2(2, 64, 64, 512, 256, 3))
+    assert len(up["tiles"]) == 4 and up["ksplit"] == 1
